@@ -1,0 +1,174 @@
+/*
+ * up3d.h -- C ABI of libunipre3d_b200.so: the B200 (sm_100a) render-loss hot path of UniPre3D.
+ *
+ * Drop-in boundary.  Plain pointers + sizes + a cudaStream_t; no torch types.
+ * Every entry point returns 0 on success and a non-zero status on error, with a human-readable
+ * message available from up3d_last_error() (thread-local).  The reference's own native ABI never
+ * reports errors (it exit(-1)s the process: pointnet2_batch/src/sampling_gpu.cu:46-50,
+ * ball_query.cpp:14-26); the external rasterizer throws std::runtime_error -- the Python host
+ * layer turns a non-zero status into RuntimeError to keep that behaviour.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _h.  The caller owns all memory,
+ *     including workspaces whose size comes from the *_bytes() queries.  No hidden
+ *     synchronisation, no allocation: every call only enqueues work on `stream`.
+ *   - Thread-safe for distinct streams and distinct buffers.
+ *   - float = IEEE fp32, indices int32, row-vector 4x4 matrices flat[16] exactly as the reference
+ *     passes them (dataset/shapenet.py:303-316).
+ */
+#ifndef UP3D_H
+#define UP3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *up3d_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define UP3D_API __attribute__((visibility("default")))
+#else
+#define UP3D_API
+#endif
+
+UP3D_API const char *up3d_last_error(void);
+UP3D_API int up3d_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Point ops.  Replace the pybind functions of
+ * /root/reference/openpoints/cpp/pointnet2_batch/src/pointnet2_api.cpp:10-24 .
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces furthest_point_sampling_wrapper (sampling.cpp:39-48; kernel sampling_gpu.cu:100-216).
+ * xyz (B,N,3) -> idx (B,M) int32.  Index sequence (first index 0, tie-breaking of the reference's
+ * block reduction for its block size opt_n_threads(N)) is reproduced bit-for-bit.
+ * `temp` (B,N) floats is scratch (the reference's 1e10-filled buffer, subsample.py:93); it is
+ * initialised internally and may be NULL when N <= up3d_fps_max_resident_points(). */
+UP3D_API int up3d_fps(int B, int N, int M, const float *xyz, float *temp, int32_t *idx, up3d_stream_t stream);
+UP3D_API int up3d_fps_max_resident_points(void);
+
+/* replaces ball_query_wrapper_fast (ball_query.cpp:29-39; kernel ball_query_gpu.cu:15-51).
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample) int32: first nsample indices (ascending)
+ * with d^2 < radius^2, padded with the first hit, all-zero when there is no hit. */
+UP3D_API int up3d_ball_query(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
+                    int32_t *idx, up3d_stream_t stream);
+
+/* replaces group_points_wrapper_fast / group_points_grad_wrapper_fast (group_points.cpp:13-35;
+ * kernels group_points_gpu.cu:14-72).  points (B,C,N), idx (B,M,K) -> out (B,C,M,K);
+ * grad_out (B,C,M,K) -> grad_points (B,C,N) (zero-filled by the call, then scatter-added). */
+UP3D_API int up3d_group_points(int B, int C, int N, int M, int K, const float *points, const int32_t *idx, float *out,
+                      up3d_stream_t stream);
+UP3D_API int up3d_group_points_grad(int B, int C, int N, int M, int K, const float *grad_out, const int32_t *idx,
+                           float *grad_points, up3d_stream_t stream);
+
+/* replaces gather_points_wrapper_fast / gather_points_grad_wrapper_fast (sampling.cpp:9-36;
+ * kernels sampling_gpu.cu:15-70).  points (B,C,N), idx (B,M) -> out (B,C,M). */
+UP3D_API int up3d_gather_points(int B, int C, int N, int M, const float *points, const int32_t *idx, float *out,
+                       up3d_stream_t stream);
+UP3D_API int up3d_gather_points_grad(int B, int C, int N, int M, const float *grad_out, const int32_t *idx,
+                            float *grad_points, up3d_stream_t stream);
+
+/* Fused SubsampleGroup tail (openpoints/models/layers/group_embed.py:39-57 + group.py:235-255):
+ * centres = xyz[fps_idx]; idx = ball_query(radius, K, xyz, centres);
+ * neighborhood[b, :, g, k] = xyz[b, idx[b,g,k], :] - centres[b, g, :]   -> (B,3,G,K)
+ * One launch instead of gather + ball_query + transpose + group + subtract.
+ * center (B,G,3) and idx (B,G,K) are also written (idx may be NULL). */
+UP3D_API int up3d_subsample_group(int B, int N, int G, int K, float radius, const float *xyz, const int32_t *fps_idx,
+                         float *center, float *neighborhood, int32_t *idx, up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Differentiable 3DGS rasterizer, batched over views.
+ * Replaces _C.rasterize_gaussians / _C.rasterize_gaussians_backward of the external
+ * diff_gaussian_rasterization package the reference binds at gaussian_renderer/__init__.py:8
+ * (called per (object, view) from train_network.py:418-442).  One call renders ALL views of
+ * ALL Gaussian sets (objects / scenes) of a step.
+ *
+ * Gaussian sets are concatenated: set s owns Gaussians [set_offsets[s], set_offsets[s+1]).
+ * Views are grouped by set: set s owns views [set_view_start[s], set_view_start[s+1]).
+ * "Records" are (view, Gaussian-of-its-set) pairs: view v owns records
+ * [view_rec_start[v], view_rec_start[v+1]); n_records = view_rec_start[n_views].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct up3d_raster_desc {
+    int32_t n_sets;
+    int32_t n_views;
+    int32_t n_gaussians;   /* total over sets */
+    int32_t n_records;     /* total (view, gaussian) pairs */
+    int32_t max_set_size;  /* max Gaussians in one set */
+    int32_t width, height;
+    int32_t sh_degree;     /* active degree D (cfg.model.max_sh_degree) */
+    int32_t sh_coeffs;     /* M = shs.size(1); 0 when colors_precomp is used */
+    int32_t antialiasing;  /* reference passes True (gaussian_renderer/__init__.py:58) */
+    float tanfovx, tanfovy;
+    float scale_modifier;
+    /* device int32 index arrays described above */
+    const int32_t *set_offsets;     /* n_sets + 1 */
+    const int32_t *set_view_start;  /* n_sets + 1 */
+    const int32_t *view_set;        /* n_views */
+    const int32_t *view_rec_start;  /* n_views + 1 */
+} up3d_raster_desc;
+
+/* bytes of the opaque forward state the caller must keep alive until the backward call
+ * (the role of upstream's geomBuffer / binningBuffer / imgBuffer). */
+UP3D_API size_t up3d_raster_state_bytes(const up3d_raster_desc *d);
+/* bytes of transient scratch for forward / backward (may be reused across calls). */
+UP3D_API size_t up3d_raster_scratch_bytes(const up3d_raster_desc *d);
+
+/* Forward.  Inputs: means3D (n_gaussians,3), shs (n_gaussians,M,3) or NULL, colors_precomp
+ * (n_gaussians,3) or NULL (exactly one), opacities (n_gaussians), scales (n_gaussians,3),
+ * rotations (n_gaussians,4), viewmats/projmats (n_views,16), campos (n_views,3), bg (3).
+ * Outputs: out_color (n_views,3,H,W), radii (n_records) int32, invdepth (n_views,1,H,W) or NULL. */
+UP3D_API int up3d_raster_forward(const up3d_raster_desc *d, const float *means3D, const float *shs,
+                        const float *colors_precomp, const float *opacities, const float *scales,
+                        const float *rotations, const float *viewmats, const float *projmats, const float *campos,
+                        const float *bg, float *out_color, int32_t *radii, float *invdepth, void *state,
+                        void *scratch, up3d_stream_t stream);
+
+/* Backward.  dL_dcolor (n_views,3,H,W).  Gradient outputs are overwritten (not accumulated):
+ * dL_dmeans3D (n_gaussians,3), dL_dshs (n_gaussians,M,3) or NULL, dL_dcolors (n_gaussians,3) or NULL,
+ * dL_dopacities (n_gaussians), dL_dscales (n_gaussians,3), dL_drotations (n_gaussians,4);
+ * dL_dmeans2D (n_records,3) or NULL -- the per-render screen-space gradient upstream returns
+ * for `means2D` (x*0.5W, y*0.5H, 0).  Sums over the views of a set are done in a fixed order
+ * (deterministic given the blend partials). */
+UP3D_API int up3d_raster_backward(const up3d_raster_desc *d, const float *means3D, const float *shs,
+                         const float *colors_precomp, const float *opacities, const float *scales,
+                         const float *rotations, const float *viewmats, const float *projmats, const float *campos,
+                         const float *bg, const float *dL_dcolor, const void *state, void *scratch,
+                         float *dL_dmeans3D, float *dL_dmeans2D, float *dL_dshs, float *dL_dcolors,
+                         float *dL_dopacities, float *dL_dscales, float *dL_drotations, up3d_stream_t stream);
+
+/* Debug accessors for the parity tests (materialise what the reference's binning buffer holds).
+ * All outputs optional (NULL to skip):
+ *   n_visible (n_views) int32            -- depth-sorted, un-culled Gaussians per view
+ *   sorted_ids (n_records) int32         -- per view: local Gaussian ids in (depth, id) order
+ *   depths (n_records) f32, xy (n_records,2), conic_opacity (n_records,4), rgb (n_records,3),
+ *   rects (n_records,4) int32            -- per record, UNSORTED (indexed by local id), 0 if culled
+ *   final_T (n_views,H,W) f32, n_contrib (n_views,H,W) int32 */
+UP3D_API int up3d_raster_debug_state(const up3d_raster_desc *d, const void *state, int32_t *n_visible, int32_t *sorted_ids,
+                            float *depths, float *xy, float *conic_opacity, float *rgb, int32_t *rects,
+                            float *final_T, int32_t *n_contrib, up3d_stream_t stream);
+
+/* Per-tile lists exactly as the reference's global (tile|depth) sort would produce them.
+ * tile_counts (n_views, tiles) int32 is always written; when tile_lists != NULL the ids of tile t of
+ * view v are written at tile_lists[view_list_start_h-style offsets]: the caller passes
+ * tile_offsets (n_views*tiles + 1) int32 = exclusive scan of a previous tile_counts query. */
+UP3D_API int up3d_raster_debug_tile_lists(const up3d_raster_desc *d, const void *state, int32_t *tile_counts,
+                                 const int32_t *tile_offsets, int32_t *tile_lists, up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused loss (train_network.py:260-302 + utils/loss_utils.py:23-45): focal-L2 between
+ * rendered (V,3,H,W) and gt (V,3,H,W); writes the scalar mean loss (loss_out[0]) and
+ * dL/drendered (same shape as rendered, may be NULL) in one pass. bg (3) is the background colour the
+ * reference compares gt against (isclose, atol 1e-6 + rtol 1e-5*|bg|).
+ * loss_out must be an 8-byte-aligned buffer of 4 floats: [0] = result, [2..3] = fp64 accumulator scratch.
+ * ---------------------------------------------------------------------------------------- */
+UP3D_API int up3d_focal_l2_loss(int64_t n_images, int H, int W, const float *rendered, const float *gt, const float *bg,
+                       float non_bg_rate, float bg_rate, float *loss_out, float *dL_drendered,
+                       up3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UP3D_H */

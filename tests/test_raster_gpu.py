@@ -1,0 +1,294 @@
+"""Parity of the sm_100a rasterizer (through the C ABI) against the CPU oracle.
+
+Tolerances (fp32, stated per north_star):
+  - tile assignment / depth order / per-tile lists / radii / rects / depth bits / pixel centres / conics: BIT-EXACT
+  - colours (SH), images: |d| <= 2e-5 absolute
+  - gradients: |d| <= 2e-4 * max|ref| + 1e-6  (float atomics / summation order differ by design)
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import make_camera, make_gaussians, oracle_scene
+
+pytestmark = pytest.mark.gpu
+
+IMG_ATOL = 2e-5
+GRAD_RTOL = 2e-4
+
+
+def _dev(a, dtype=torch.float32):
+    return torch.tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+def _kw(c, W, H, deg):
+    return dict(image_height=H, image_width=W, tanfovx=c["tanfovx"], tanfovy=c["tanfovy"], sh_degree=deg)
+
+
+def _tensors(g, c, bg, requires_grad=False):
+    t = {k: _dev(v).requires_grad_(requires_grad) for k, v in g.items()}
+    cam = dict(viewmats=_dev(c["view"]).reshape(1, 4, 4), projmats=_dev(c["proj"]).reshape(1, 4, 4),
+               campos=_dev(c["campos"]).reshape(1, 3), bg=_dev(np.asarray(bg, np.float32)))
+    return t, cam
+
+
+CASES = [
+    # regime, P, W, H, deg, M, bg
+    ("reference", 128, 128, 128, 1, 4, (0, 0, 0)),
+    ("reference", 300, 96, 80, 1, 4, (1, 1, 1)),
+    ("mid", 500, 100, 70, 3, 16, (0.2, 0.5, 0.7)),
+    ("small", 3000, 128, 128, 2, 9, (0, 0, 0)),
+    ("small", 1000, 37, 53, 0, 1, (0.1, 0.1, 0.1)),
+    ("mid", 2000, 256, 256, 1, 4, (0, 0, 0)),
+]
+
+
+@pytest.mark.parametrize("regime,P,W,H,deg,M,bg", CASES)
+def test_forward_geometry_lists_image(oracle, regime, P, W, H, deg, M, bg):
+    from unipre3d_b200.rasterizer import debug_forward_state
+    g = make_gaussians(P, seed=P + W, regime=regime, sh_coeffs=M)
+    c = make_camera(az=33.0, el=21.0)
+    sc = oracle_scene(g, c, W, H, sh_degree=deg, bg=bg)
+    geo = oracle.preprocess(sc)
+    keys, pl, ranges = oracle.bin_tiles(sc, geo)
+    color, fT, nc = oracle.blend_forward(sc, geo, pl, ranges)
+
+    t, cam = _tensors(g, c, bg)
+    out = debug_forward_state(t["means3D"], t["opacities"], t["scales"], t["rotations"], cam["viewmats"],
+                              cam["projmats"], cam["campos"], cam["bg"], set_sizes=[P], views_per_set=[1],
+                              shs=t["shs"], **_kw(c, W, H, deg))
+    torch.cuda.synchronize()
+    radii = out["radii"].cpu().numpy()
+    assert np.array_equal(radii, geo.radii[:P]), "radii differ"
+    vis = radii > 0
+    assert int(out["n_visible"][0]) == int(vis.sum())
+    assert np.array_equal(out["rects"].cpu().numpy()[:P][vis], geo.rect[:P][vis]), "tile rectangles differ"
+    d = out["depths"].cpu().numpy()[:P]
+    assert np.array_equal(d[vis].view(np.uint32), geo.depth[:P][vis].view(np.uint32)), "depth bits differ"
+    assert np.array_equal(out["xy"].cpu().numpy()[:P][vis].view(np.uint32), geo.xy[:P][vis].view(np.uint32))
+    assert np.array_equal(out["conic_opacity"].cpu().numpy()[:P][vis].view(np.uint32),
+                          geo.conic_opacity[:P][vis].view(np.uint32)), "conic/opacity bits differ"
+    np.testing.assert_allclose(out["rgb"].cpu().numpy()[:P][vis], geo.rgb[:P][vis], atol=2e-6, rtol=0)
+    # per-tile lists == the reference's global (tile|depth) sort, entry for entry
+    counts = out["tile_counts"].cpu().numpy()[0]
+    assert np.array_equal(counts, (ranges[:, 1] - ranges[:, 0]).astype(np.int64)), "tiles_touched per tile differ"
+    assert np.array_equal(out["tile_lists"].cpu().numpy()[: len(pl)], pl.astype(np.int32)), "tile lists differ"
+    # depth-sorted ids: stable by (depth bits, id)
+    ids = out["sorted_ids"].cpu().numpy()[: int(vis.sum())]
+    order = np.lexsort((np.arange(P)[vis], geo.depth[:P][vis].view(np.uint32)))
+    assert np.array_equal(ids, np.arange(P)[vis][order])
+    # image
+    np.testing.assert_allclose(out["color"][0].cpu().numpy(), color, atol=IMG_ATOL, rtol=0)
+    np.testing.assert_allclose(out["final_T"][0].cpu().numpy(), fT, atol=IMG_ATOL, rtol=0)
+    mism = (out["n_contrib"][0].cpu().numpy() != nc.astype(np.int32)).mean()
+    assert mism <= 2e-3, f"n_contrib mismatching pixels: {mism}"
+
+
+@pytest.mark.parametrize("regime,P,W,H,deg,M,bg", CASES)
+def test_backward_matches_oracle(oracle, regime, P, W, H, deg, M, bg):
+    from unipre3d_b200.rasterizer import rasterize_batch
+    g = make_gaussians(P, seed=P + W, regime=regime, sh_coeffs=M)
+    c = make_camera(az=-70.0, el=35.0)
+    sc = oracle_scene(g, c, W, H, sh_degree=deg, bg=bg)
+    rng = np.random.default_rng(P)
+    dL = rng.normal(size=(3, H, W)).astype(np.float32)
+    ref = oracle.render(sc, dL)
+    t, cam = _tensors(g, c, bg, requires_grad=True)
+    m2d = torch.zeros((P, 3), device="cuda", requires_grad=True)
+    color, radii, invdepth = rasterize_batch(t["means3D"], t["opacities"], t["scales"], t["rotations"], cam["viewmats"],
+                                             cam["projmats"], cam["campos"], cam["bg"], set_sizes=[P], views_per_set=[1],
+                                             shs=t["shs"], means2D=m2d, **_kw(c, W, H, deg))
+    np.testing.assert_allclose(color[0].detach().cpu().numpy(), ref["color"], atol=IMG_ATOL, rtol=0)
+    (color[0] * _dev(dL)).sum().backward()
+    names = dict(means3D="means3D", opacities="opacities", scales="scales", rotations="rotations", shs="shs")
+    for k, rk in names.items():
+        a = t[k].grad.cpu().numpy().reshape(ref["grads"][rk].shape)
+        b = ref["grads"][rk]
+        tol = GRAD_RTOL * np.abs(b).max() + 1e-6
+        assert np.abs(a - b).max() <= tol, f"{k}: max diff {np.abs(a - b).max()} > {tol}"
+    a, b = m2d.grad.cpu().numpy(), ref["grads"]["means2D"]
+    assert np.abs(a - b).max() <= GRAD_RTOL * np.abs(b).max() + 1e-6
+
+
+def test_batch_equals_single_views_and_grads_sum(oracle):
+    """3 sets x 2 views in one call == 6 oracle renders; gradients are the sum over each set's views."""
+    from unipre3d_b200.rasterizer import rasterize_batch
+    W = H = 64
+    sizes, V = [150, 1, 260], 2
+    gs = [make_gaussians(p, seed=10 + i, regime="mid") for i, p in enumerate(sizes)]
+    cams = [[make_camera(az=40.0 * (2 * i + j), el=10.0 + 15 * j) for j in range(V)] for i in range(3)]
+    bg = (0.3, 0.1, 0.6)
+    rng = np.random.default_rng(0)
+    dL = rng.normal(size=(len(sizes) * V, 3, H, W)).astype(np.float32)
+    cat = {k: np.concatenate([g[k] for g in gs], 0) for k in gs[0]}
+    t = {k: _dev(v).requires_grad_(True) for k, v in cat.items()}
+    vm = _dev(np.stack([c["view"] for cs in cams for c in cs]))
+    pm = _dev(np.stack([c["proj"] for cs in cams for c in cs]))
+    cp = _dev(np.stack([c["campos"] for cs in cams for c in cs]))
+    c0 = cams[0][0]
+    color, radii, _ = rasterize_batch(t["means3D"], t["opacities"], t["scales"], t["rotations"], vm, pm, cp, _dev(bg),
+                                      set_sizes=sizes, views_per_set=[V] * 3, shs=t["shs"], **_kw(c0, W, H, 1))
+    (color * _dev(dL)).sum().backward()
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    rec = 0
+    for i, g in enumerate(gs):
+        acc = None
+        for j in range(V):
+            sc = oracle_scene(g, cams[i][j], W, H, sh_degree=1, bg=bg)
+            ref = oracle.render(sc, dL[i * V + j])
+            np.testing.assert_allclose(color[i * V + j].detach().cpu().numpy(), ref["color"], atol=IMG_ATOL, rtol=0)
+            assert np.array_equal(radii[rec: rec + sizes[i]].cpu().numpy(), ref["radii"])
+            rec += sizes[i]
+            acc = ref["grads"] if acc is None else {k: acc[k] + ref["grads"][k] for k in acc}
+        for k in ["means3D", "opacities", "scales", "rotations", "shs"]:
+            a = t[k].grad[off[i]: off[i + 1]].cpu().numpy().reshape(acc[k].shape)
+            tol = GRAD_RTOL * np.abs(acc[k]).max() + 1e-6
+            assert np.abs(a - acc[k]).max() <= tol, (i, k)
+
+
+def test_colors_precomp_and_white_bg(oracle):
+    from unipre3d_b200.rasterizer import rasterize_batch
+    P, W, H = 400, 80, 48
+    g = make_gaussians(P, seed=3, regime="mid")
+    c = make_camera(az=10, el=50)
+    col = np.random.default_rng(1).uniform(0, 1, (P, 3)).astype(np.float32)
+    sc = oracle_scene(g, c, W, H, sh_degree=0, bg=(1, 1, 1), colors_precomp=col)
+    dL = np.random.default_rng(2).normal(size=(3, H, W)).astype(np.float32)
+    ref = oracle.render(sc, dL)
+    t, cam = _tensors(g, c, (1, 1, 1), requires_grad=True)
+    colt = _dev(col).requires_grad_(True)
+    color, _, _ = rasterize_batch(t["means3D"], t["opacities"], t["scales"], t["rotations"], cam["viewmats"],
+                                  cam["projmats"], cam["campos"], cam["bg"], set_sizes=[P], views_per_set=[1],
+                                  colors_precomp=colt, **_kw(c, W, H, 0))
+    np.testing.assert_allclose(color[0].detach().cpu().numpy(), ref["color"], atol=IMG_ATOL, rtol=0)
+    (color[0] * _dev(dL)).sum().backward()
+    b = ref["grads"]["colors"]
+    assert np.abs(colt.grad.cpu().numpy() - b).max() <= GRAD_RTOL * np.abs(b).max() + 1e-6
+
+
+def test_all_culled_and_behind_camera(oracle):
+    from unipre3d_b200.rasterizer import rasterize_batch
+    P, W, H = 64, 32, 32
+    g = make_gaussians(P, seed=4, regime="mid")
+    g["means3D"][:, :] += np.array([0, 50.0, 0], np.float32)  # far behind / outside
+    c = make_camera(az=0, el=0)
+    sc = oracle_scene(g, c, W, H, bg=(0.25, 0.5, 0.75))
+    ref = oracle.render(sc)
+    t, cam = _tensors(g, c, (0.25, 0.5, 0.75), requires_grad=True)
+    color, radii, _ = rasterize_batch(t["means3D"], t["opacities"], t["scales"], t["rotations"], cam["viewmats"],
+                                      cam["projmats"], cam["campos"], cam["bg"], set_sizes=[P], views_per_set=[1],
+                                      shs=t["shs"], **_kw(c, W, H, 1))
+    assert np.array_equal(radii.cpu().numpy(), ref["radii"])
+    np.testing.assert_allclose(color[0].detach().cpu().numpy(), ref["color"], atol=IMG_ATOL, rtol=0)
+    color.sum().backward()
+    if (ref["radii"] > 0).sum() == 0:
+        assert float(t["means3D"].grad.abs().max()) == 0.0
+
+
+def test_large_set_uses_global_sort_path(oracle):
+    """P > 12288 leaves the shared-memory sort; lists must still be bit-exact."""
+    from unipre3d_b200.rasterizer import debug_forward_state
+    P, W, H = 20000, 128, 96
+    g = make_gaussians(P, seed=8, regime="small")
+    c = make_camera(az=123, el=15)
+    sc = oracle_scene(g, c, W, H, sh_degree=1)
+    geo = oracle.preprocess(sc)
+    keys, pl, ranges = oracle.bin_tiles(sc, geo)
+    color, fT, nc = oracle.blend_forward(sc, geo, pl, ranges)
+    t, cam = _tensors(g, c, (0, 0, 0))
+    out = debug_forward_state(t["means3D"], t["opacities"], t["scales"], t["rotations"], cam["viewmats"],
+                              cam["projmats"], cam["campos"], cam["bg"], set_sizes=[P], views_per_set=[1],
+                              shs=t["shs"], **_kw(c, W, H, 1))
+    assert np.array_equal(out["tile_lists"].cpu().numpy()[: len(pl)], pl.astype(np.int32))
+    np.testing.assert_allclose(out["color"][0].cpu().numpy(), color, atol=IMG_ATOL, rtol=0)
+
+
+def test_duplicate_depths_keep_ascending_id_order(oracle):
+    """Ties (equal tile, equal depth bits) must keep ascending Gaussian id (stable sort) -- A.4."""
+    from unipre3d_b200.rasterizer import debug_forward_state
+    P, W, H = 512, 64, 64
+    g = make_gaussians(P, seed=9, regime="mid")
+    g["means3D"][1::2] = g["means3D"][0::2]  # pairs share a centre -> identical depth
+    c = make_camera(az=5, el=5)
+    sc = oracle_scene(g, c, W, H)
+    geo = oracle.preprocess(sc)
+    keys, pl, ranges = oracle.bin_tiles(sc, geo)
+    t, cam = _tensors(g, c, (0, 0, 0))
+    out = debug_forward_state(t["means3D"], t["opacities"], t["scales"], t["rotations"], cam["viewmats"],
+                              cam["projmats"], cam["campos"], cam["bg"], set_sizes=[P], views_per_set=[1],
+                              shs=t["shs"], **_kw(c, W, H, 1))
+    assert np.array_equal(out["tile_lists"].cpu().numpy()[: len(pl)], pl.astype(np.int32))
+
+
+def test_full_size_properties_headline_config():
+    """BASELINE config 2 raster sizes (8 objects x 4 views, P=8192, 256x256): size-independent properties."""
+    from unipre3d_b200.rasterizer import debug_forward_state, rasterize_batch
+    B, V, P, W, H = 8, 4, 8192, 256, 256
+    gs = [make_gaussians(P, seed=100 + i, regime="reference") for i in range(B)]
+    cat = {k: _dev(np.concatenate([g[k] for g in gs], 0)) for k in gs[0]}
+    cams = [make_camera(az=360.0 * i / (B * V), el=5 + 2.0 * i) for i in range(B * V)]
+    vm, pm = _dev(np.stack([c["view"] for c in cams])), _dev(np.stack([c["proj"] for c in cams]))
+    cp = _dev(np.stack([c["campos"] for c in cams]))
+    kw = _kw(cams[0], W, H, 1)
+    out = debug_forward_state(cat["means3D"], cat["opacities"], cat["scales"], cat["rotations"], vm, pm, cp,
+                              _dev([0, 0, 0]), set_sizes=[P] * B, views_per_set=[V] * B, shs=cat["shs"], tile_lists=False,
+                              **kw)
+    nvis = out["n_visible"].cpu().numpy()
+    depths, ids = out["depths"].cpu().numpy(), out["sorted_ids"].cpu().numpy()
+    for v in range(B * V):
+        d = depths[v * P:(v + 1) * P][ids[v * P: v * P + nvis[v]]]
+        assert np.all(np.diff(d) >= 0), "depth order not sorted"
+        assert len(np.unique(ids[v * P: v * P + nvis[v]])) == nvis[v], "sorted ids are not a permutation"
+    img = out["color"].cpu().numpy()
+    assert np.isfinite(img).all()
+    fT = out["final_T"].cpu().numpy()
+    assert (fT >= 0).all() and (fT <= 1).all()
+    assert (out["n_contrib"].cpu().numpy() <= nvis[:, None, None]).all()
+    # linearity of the backward in dL/dcolor (the backward pass is linear in the incoming gradient)
+    t = {k: v.clone().requires_grad_(True) for k, v in cat.items()}
+    color, _, _ = rasterize_batch(t["means3D"], t["opacities"], t["scales"], t["rotations"], vm, pm, cp, _dev([0, 0, 0]),
+                                  set_sizes=[P] * B, views_per_set=[V] * B, shs=t["shs"], **kw)
+    w = torch.randn_like(color)
+    g1 = torch.autograd.grad((color * w).sum(), t["means3D"], retain_graph=True)[0]
+    g2 = torch.autograd.grad((color * (2.5 * w)).sum(), t["means3D"])[0]
+    assert torch.isfinite(g1).all()
+    assert float((g2 - 2.5 * g1).abs().max()) <= 1e-3 * float(g1.abs().max()) + 1e-6
+
+
+def test_render_predicted_dropin_matches_batch_and_errors():
+    from types import SimpleNamespace as NS
+    from unipre3d_b200.gaussian_renderer import render_batch_predicted, render_predicted
+    from unipre3d_b200.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    cfg = NS(data=NS(fov=49.13434264120263, training_resolution=64), model=NS(max_sh_degree=1))
+    B, V, P = 2, 3, 96
+    gs = [make_gaussians(P, seed=50 + i) for i in range(B)]
+    pc = {"xyz": _dev(np.stack([g["means3D"] for g in gs])), "opacity": _dev(np.stack([g["opacities"] for g in gs]))[..., None],
+          "scaling": _dev(np.stack([g["scales"] for g in gs])), "rotation": _dev(np.stack([g["rotations"] for g in gs])),
+          "features_dc": _dev(np.stack([g["shs"][:, :1] for g in gs])), "features_rest": _dev(np.stack([g["shs"][:, 1:] for g in gs]))}
+    cams = [[make_camera(az=30 * (i * V + j), el=12) for j in range(V)] for i in range(B)]
+    wv = _dev(np.stack([[c["view"] for c in cs] for cs in cams]))
+    fp = _dev(np.stack([[c["proj"] for c in cs] for cs in cams]))
+    cc = _dev(np.stack([[c["campos"] for c in cs] for cs in cams]))
+    bg = _dev([0, 0, 0])
+    batch = render_batch_predicted(pc, wv, fp, cc, bg, cfg)
+    for b in range(B):
+        one = {k: v[b].contiguous() for k, v in pc.items()}
+        for r in range(V):
+            o = render_predicted(one, wv[b, r], fp[b, r], cc[b, r], bg, cfg)
+            assert o["render"].shape == (3, 64, 64)
+            assert torch.equal(o["render"], batch["render"][b, r])
+            assert torch.equal(o["radii"], batch["radii"][b][r])
+            assert o["visibility_filter"].dtype == torch.bool
+    o["render"].sum().backward() if o["render"].requires_grad else None
+    rs = GaussianRasterizationSettings(64, 64, 0.45, 0.45, bg, 1.0, wv[0, 0], fp[0, 0], 1, cc[0, 0], False, False, True)
+    rast = GaussianRasterizer(rs)
+    one = {k: v[0].contiguous() for k, v in pc.items()}
+    with pytest.raises(Exception, match="excatly one"):
+        rast(means3D=one["xyz"], means2D=None, opacities=one["opacity"], scales=one["scaling"], rotations=one["rotation"])
+    with pytest.raises(Exception, match="exactly one"):
+        rast(means3D=one["xyz"], means2D=None, opacities=one["opacity"], shs=one["features_dc"])
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        rast(means3D=one["xyz"].cpu(), means2D=None, opacities=one["opacity"].cpu(), shs=one["features_dc"].cpu(),
+             scales=one["scaling"].cpu(), rotations=one["rotation"].cpu())

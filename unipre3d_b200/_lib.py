@@ -1,0 +1,91 @@
+"""ctypes binding of libunipre3d_b200.so (the C ABI declared in include/up3d.h).
+
+There is NO CPU fallback: if the shared library is missing and cannot be built, importing this
+module raises; if a tensor is not on a CUDA device the host wrappers raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libunipre3d_b200.so")
+
+
+class RasterDesc(C.Structure):
+    """struct up3d_raster_desc (include/up3d.h)."""
+    _fields_ = [("n_sets", C.c_int32), ("n_views", C.c_int32), ("n_gaussians", C.c_int32), ("n_records", C.c_int32),
+                ("max_set_size", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("sh_degree", C.c_int32),
+                ("sh_coeffs", C.c_int32), ("antialiasing", C.c_int32), ("tanfovx", C.c_float), ("tanfovy", C.c_float),
+                ("scale_modifier", C.c_float),
+                ("set_offsets", C.c_void_p), ("set_view_start", C.c_void_p), ("view_set", C.c_void_p),
+                ("view_rec_start", C.c_void_p)]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        # in-tree build (nvcc cross-compiles without a GPU); fails loudly when nvcc is absent
+        from .csrc.build import build_library
+        build_library()
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    D = C.POINTER(RasterDesc)
+    sigs = {
+        "up3d_last_error": (C.c_char_p, []),
+        "up3d_version": (i32, []),
+        "up3d_fps": (i32, [i32, i32, i32, vp, vp, vp, vp]),
+        "up3d_fps_max_resident_points": (i32, []),
+        "up3d_ball_query": (i32, [i32, i32, i32, f32, i32, vp, vp, vp, vp]),
+        "up3d_group_points": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "up3d_group_points_grad": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "up3d_gather_points": (i32, [i32, i32, i32, i32, vp, vp, vp, vp]),
+        "up3d_gather_points_grad": (i32, [i32, i32, i32, i32, vp, vp, vp, vp]),
+        "up3d_subsample_group": (i32, [i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+        "up3d_raster_state_bytes": (C.c_size_t, [D]),
+        "up3d_raster_scratch_bytes": (C.c_size_t, [D]),
+        "up3d_raster_forward": (i32, [D] + [vp] * 16),
+        "up3d_raster_backward": (i32, [D] + [vp] * 21),
+        "up3d_raster_debug_state": (i32, [D] + [vp] * 11),
+        "up3d_raster_debug_tile_lists": (i32, [D] + [vp] * 5),
+        "up3d_focal_l2_loss": (i32, [i64, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_resident_points", "up3d_ball_query",
+            "up3d_group_points", "up3d_group_points_grad", "up3d_gather_points", "up3d_gather_points_grad",
+            "up3d_subsample_group", "up3d_raster_state_bytes", "up3d_raster_scratch_bytes", "up3d_raster_forward",
+            "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_focal_l2_loss"]
+
+# kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def check(status: int, launches: int = 0) -> None:
+    """Non-zero status -> RuntimeError carrying up3d_last_error() (the external rasterizer the reference
+    uses raises std::runtime_error -> RuntimeError; we keep that error type)."""
+    global launch_count
+    if status != 0:
+        raise RuntimeError(lib.up3d_last_error().decode("utf-8", "replace"))
+    launch_count += launches
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("unipre3d_b200: tensors must live on a CUDA device (there is no CPU fallback); "
+                               f"got device {t.device}")

@@ -1,0 +1,333 @@
+// pointops.cu -- FPS / ball query / grouping / gather for sm_100a.
+//
+// Replaces /root/reference/openpoints/cpp/pointnet2_batch/src/{sampling_gpu.cu,ball_query_gpu.cu,
+// group_points_gpu.cu} (pybind surface pointnet2_api.cpp:10-24).  Index outputs are bit-identical to the
+// reference kernels, including its tie-breaking (see fps_priority below); the squared distance uses the
+// exact operation order nvcc emits for the reference source: d = fma(dz,dz, fma(dx,dx, dy*dy)).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace up3d {
+
+// ------------------------------------------------------------------------------------------------
+// Furthest point sampling.
+//   reference: one CTA of bs = opt_n_threads(N) threads per cloud; every round re-reads all points and
+//   the (B,N) temp array from global memory and runs a 10-level __syncthreads tree (sampling_gpu.cu:125-215).
+//   here: the cloud and its running min-distances live in REGISTERS (PPT points per thread), the query
+//   point is read from a shared-memory copy, the arg-max is two REDUX instructions per level and ONE
+//   __syncthreads per round (double-buffered partials).
+//
+// Tie-breaking of the reference, reproduced exactly: thread t scans k = t, t+bs, ... keeping the first
+// maximum (strict >); the tree merges slot i with slot i+s keeping the lower slot on ties.  The winner among
+// equal distances is therefore the point with the smallest (bitreverse_{log2 bs}(k mod bs), k div bs).
+// We fold that into the low word of a 64-bit key so that a plain max-reduction yields the same index.
+// ------------------------------------------------------------------------------------------------
+constexpr int FPS_THREADS = 1024;
+constexpr int FPS_MAX_PPT = 16;
+
+__device__ __forceinline__ uint32_t fps_priority(int k, int bs, int log2bs) {
+    const uint32_t low = (uint32_t)(k & (bs - 1));
+    const uint32_t rev = log2bs ? (__brev(low) >> (32 - log2bs)) : 0u;
+    return 0xFFFFFFFFu - ((rev << 20) | (uint32_t)(k >> log2bs));
+}
+__device__ __forceinline__ int fps_index_from_priority(uint32_t inv, int bs, int log2bs) {
+    const uint32_t p = 0xFFFFFFFFu - inv;
+    const uint32_t rev = p >> 20, q = p & 0xFFFFFu;
+    const uint32_t low = log2bs ? (__brev(rev) >> (32 - log2bs)) : 0u;
+    return (int)(q * (uint32_t)bs + low);
+}
+
+// block-wide arg-max of (hi, lo) with hi compared first; result broadcast to every thread
+__device__ __forceinline__ void block_argmax(uint32_t &hi, uint32_t &lo, uint32_t (*red)[2], int lane, int warp,
+                                             int nwarps) {
+    uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    if (lane == 0) { red[warp][0] = mh; red[warp][1] = ml; }
+    __syncthreads();
+    uint32_t h2 = lane < nwarps ? red[lane][0] : 0u, l2 = lane < nwarps ? red[lane][1] : 0u;
+    mh = __reduce_max_sync(0xffffffffu, h2);
+    ml = __reduce_max_sync(0xffffffffu, h2 == mh ? l2 : 0u);
+    hi = mh; lo = ml;
+}
+
+template <int PPT, bool REG_COORDS>
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_resident_kernel(int N, int M, int bs, int log2bs, const float *__restrict__ xyz, int32_t *__restrict__ idxs) {
+    extern __shared__ float s_pts[];  // [3][N]
+    __shared__ uint32_t red[2][32][2];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *ds = xyz + (size_t)b * N * 3;
+    int32_t *out = idxs + (size_t)b * M;
+    float *sx = s_pts, *sy = s_pts + N, *sz = s_pts + 2 * N;
+    // PPT <= 8: coordinates + priorities in registers; PPT == 16: only the running min-distances are
+    // (64-register budget at 1024 threads), coordinates come from the conflict-free shared copy.
+    constexpr int RP = REG_COORDS ? PPT : 1;
+    float px[RP], py[RP], pz[RP], tmp[PPT];
+    uint32_t pr[RP];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int k = tid + j * FPS_THREADS;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (k < N) {
+            x = ds[3 * k]; y = ds[3 * k + 1]; z = ds[3 * k + 2];
+            sx[k] = x; sy[k] = y; sz[k] = z;
+        }
+        if (REG_COORDS) { px[j] = x; py[j] = y; pz[j] = z; pr[j] = k < N ? fps_priority(k, bs, log2bs) : 0u; }
+        tmp[j] = 1e10f;
+    }
+    if (tid == 0) out[0] = 0;
+    __syncthreads();
+    int old = 0;
+    for (int r = 1; r < M; ++r) {
+        const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+        uint32_t bh = 0u, bl = 0u;  // every real candidate has lo >= 1 > 0 ... and hi >= 0
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const int k = tid + j * FPS_THREADS;
+            const bool valid = k < N;
+            float x2, y2, z2;
+            uint32_t p;
+            if (REG_COORDS) { x2 = px[j]; y2 = py[j]; z2 = pz[j]; p = pr[j]; }
+            else { const int kk = valid ? k : 0; x2 = sx[kk]; y2 = sy[kk]; z2 = sz[kk]; p = fps_priority(kk, bs, log2bs); }
+            const float dx = xsub(x2, x1), dy = xsub(y2, y1), dz = xsub(z2, z1);
+            const float d = xfma(dz, dz, xfma(dx, dx, xmul(dy, dy)));
+            const float d2 = fminf(d, tmp[j]);
+            tmp[j] = d2;
+            const uint32_t h = __float_as_uint(d2);
+            const bool better = valid && (h > bh || (h == bh && p > bl));
+            bh = better ? h : bh;
+            bl = better ? p : bl;
+        }
+        block_argmax(bh, bl, red[r & 1], lane, warp, FPS_THREADS / 32);
+        old = fps_index_from_priority(bl, bs, log2bs);
+        if (tid == 0) out[r] = old;
+    }
+}
+
+// streaming fallback for clouds that do not fit the register file: temp lives in global memory
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_streaming_kernel(int N, int M, int bs, int log2bs, const float *__restrict__ xyz, float *__restrict__ temp,
+                     int32_t *__restrict__ idxs) {
+    __shared__ uint32_t red[2][32][2];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *ds = xyz + (size_t)b * N * 3;
+    float *tp = temp + (size_t)b * N;
+    int32_t *out = idxs + (size_t)b * M;
+    for (int k = tid; k < N; k += FPS_THREADS) tp[k] = 1e10f;
+    if (tid == 0) out[0] = 0;
+    __syncthreads();
+    int old = 0;
+    for (int r = 1; r < M; ++r) {
+        const float x1 = ds[3 * old], y1 = ds[3 * old + 1], z1 = ds[3 * old + 2];
+        uint32_t bh = 0u, bl = 0u;
+        for (int k = tid; k < N; k += FPS_THREADS) {
+            const float dx = xsub(ds[3 * k], x1), dy = xsub(ds[3 * k + 1], y1), dz = xsub(ds[3 * k + 2], z1);
+            const float d = xfma(dz, dz, xfma(dx, dx, xmul(dy, dy)));
+            const float d2 = fminf(d, tp[k]);
+            tp[k] = d2;
+            const uint32_t h = __float_as_uint(d2), p = fps_priority(k, bs, log2bs);
+            const bool better = (h > bh || (h == bh && p > bl));
+            bh = better ? h : bh;
+            bl = better ? p : bl;
+        }
+        block_argmax(bh, bl, red[r & 1], lane, warp, FPS_THREADS / 32);
+        old = fps_index_from_priority(bl, bs, log2bs);
+        if (tid == 0) out[r] = old;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ball query (+ optional fused centre gather / grouping / centring): one WARP per query centre.
+//   reference: one THREAD per centre scanning all N points (ball_query_gpu.cu:15-51).
+//   here: 32 lanes test 32 consecutive points; ballot + popc keep the ascending-index order.
+// ------------------------------------------------------------------------------------------------
+constexpr int BQ_WARPS = 8;
+
+template <bool FUSED>
+__global__ void __launch_bounds__(BQ_WARPS * 32)
+ball_query_kernel(int N, int M, int K, float radius2, const float *__restrict__ new_xyz, const float *__restrict__ xyz,
+                  const int32_t *__restrict__ fps_idx, int32_t *__restrict__ idx_out, float *__restrict__ center_out,
+                  float *__restrict__ neigh_out) {
+    extern __shared__ int32_t s_idx[];  // [BQ_WARPS][K]
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = blockIdx.x * BQ_WARPS + warp;
+    if (m >= M) return;
+    const float *pts = xyz + (size_t)b * N * 3;
+    float cx, cy, cz;
+    if (FUSED) {
+        const int ci = fps_idx[(size_t)b * M + m];
+        cx = pts[3 * ci]; cy = pts[3 * ci + 1]; cz = pts[3 * ci + 2];
+        if (lane < 3) center_out[((size_t)b * M + m) * 3 + lane] = lane == 0 ? cx : (lane == 1 ? cy : cz);
+    } else {
+        const float *c = new_xyz + ((size_t)b * M + m) * 3;
+        cx = c[0]; cy = c[1]; cz = c[2];
+    }
+    int32_t *my = s_idx + warp * K;
+    int cnt = 0, first = 0;
+    for (int k0 = 0; k0 < N && cnt < K; k0 += 32) {
+        const int k = k0 + lane;
+        bool hit = false;
+        if (k < N) {
+            const float dx = xsub(cx, pts[3 * k]), dy = xsub(cy, pts[3 * k + 1]), dz = xsub(cz, pts[3 * k + 2]);
+            const float d2 = xfma(dz, dz, xfma(dx, dx, xmul(dy, dy)));
+            hit = d2 < radius2;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            if (cnt == 0) first = k0 + __ffs(bal) - 1;
+            const int slot = cnt + __popc(bal & lanemask_lt());
+            if (hit && slot < K) my[slot] = k;
+            cnt += __popc(bal);
+        }
+    }
+    __syncwarp();
+    cnt = min(cnt, K);
+    for (int s = lane; s < K; s += 32) {
+        // pad with the first hit; no hit at all -> zeros (the reference's zero-initialised idx, group.py:194)
+        const int id = s < cnt ? my[s] : first;
+        if (idx_out) idx_out[((size_t)b * M + m) * K + s] = id;
+        if (FUSED) {
+            const size_t o = (((size_t)b * 3) * M + m) * K + s, cs = (size_t)M * K;
+            neigh_out[o] = pts[3 * id] - cx;
+            neigh_out[o + cs] = pts[3 * id + 1] - cy;
+            neigh_out[o + 2 * cs] = pts[3 * id + 2] - cz;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// grouping / gather (+ gradients)
+// ------------------------------------------------------------------------------------------------
+__global__ void group_points_kernel(int C, int N, int M, int K, const float *__restrict__ points,
+                                    const int32_t *__restrict__ idx, float *__restrict__ out) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * K) return;
+    const int id = idx[(size_t)b * M * K + e];
+    out[((size_t)b * C + c) * M * K + e] = points[((size_t)b * C + c) * N + id];
+}
+__global__ void group_points_grad_kernel(int C, int N, int M, int K, const float *__restrict__ grad_out,
+                                         const int32_t *__restrict__ idx, float *__restrict__ grad_points) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * K) return;
+    const int id = idx[(size_t)b * M * K + e];
+    atomicAdd(grad_points + ((size_t)b * C + c) * N + id, grad_out[((size_t)b * C + c) * M * K + e]);
+}
+
+}  // namespace up3d
+
+using namespace up3d;
+
+static int ref_block_size(int n) {
+    // cuda_utils.h:10-14 of the reference, evaluated the same way (double log ratio, truncation)
+    const int pow_2 = (int)(log((double)n) / log(2.0));
+    int t = 1 << pow_2;
+    if (t > 1024) t = 1024;
+    if (t < 1) t = 1;
+    return t;
+}
+
+extern "C" {
+
+int up3d_fps_max_resident_points(void) { return FPS_THREADS * FPS_MAX_PPT; }
+
+int up3d_fps(int B, int N, int M, const float *xyz, float *temp, int32_t *idx, up3d_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UP3D_CHECK_ARG(B >= 0 && N > 0 && M >= 0, "up3d_fps: bad sizes B=%d N=%d M=%d", B, N, M);
+    UP3D_CHECK_ARG(M <= N, "up3d_fps: npoint (%d) must not exceed N (%d)", M, N);
+    if (B == 0 || M == 0) return 0;
+    UP3D_CHECK_ARG(xyz && idx, "up3d_fps: null pointer");
+    UP3D_CHECK_ARG(N < (1 << 30), "up3d_fps: N too large");
+    const int bs = ref_block_size(N);
+    int log2bs = 0;
+    while ((1 << log2bs) < bs) ++log2bs;
+    if (N <= FPS_THREADS * FPS_MAX_PPT) {
+        const size_t smem = sizeof(float) * 3 * (size_t)N;
+#define UP3D_FPS_CASE(P)                                                                                           \
+    {                                                                                                              \
+        UP3D_CUDA_OK(cudaFuncSetAttribute(fps_resident_kernel<P, (P <= 8)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fps_resident_kernel<P, (P <= 8)><<<B, FPS_THREADS, smem, stream>>>(N, M, bs, log2bs, xyz, idx);             \
+    }
+        const int ppt = div_up(N, FPS_THREADS);
+        if (ppt <= 1) UP3D_FPS_CASE(1)
+        else if (ppt <= 2) UP3D_FPS_CASE(2)
+        else if (ppt <= 4) UP3D_FPS_CASE(4)
+        else if (ppt <= 8) UP3D_FPS_CASE(8)
+        else UP3D_FPS_CASE(16)
+#undef UP3D_FPS_CASE
+        UP3D_LAUNCH_OK("fps_resident_kernel");
+    } else {
+        UP3D_CHECK_ARG(temp != nullptr, "up3d_fps: temp scratch (B,N) required when N > %d", FPS_THREADS * FPS_MAX_PPT);
+        fps_streaming_kernel<<<B, FPS_THREADS, 0, stream>>>(N, M, bs, log2bs, xyz, temp, idx);
+        UP3D_LAUNCH_OK("fps_streaming_kernel");
+    }
+    return 0;
+}
+
+int up3d_ball_query(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
+                    int32_t *idx, up3d_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UP3D_CHECK_ARG(B >= 0 && N > 0 && M >= 0 && nsample > 0, "up3d_ball_query: bad sizes B=%d N=%d M=%d nsample=%d", B, N, M, nsample);
+    if (B == 0 || M == 0) return 0;
+    UP3D_CHECK_ARG(new_xyz && xyz && idx, "up3d_ball_query: null pointer");
+    UP3D_CHECK_ARG(nsample <= 1024, "up3d_ball_query: nsample > 1024 not supported");
+    volatile float r2 = radius * radius;
+    ball_query_kernel<false><<<dim3(div_up(M, BQ_WARPS), B), BQ_WARPS * 32, sizeof(int32_t) * BQ_WARPS * nsample, stream>>>(
+        N, M, nsample, r2, new_xyz, xyz, nullptr, idx, nullptr, nullptr);
+    UP3D_LAUNCH_OK("ball_query_kernel");
+    return 0;
+}
+
+int up3d_subsample_group(int B, int N, int G, int K, float radius, const float *xyz, const int32_t *fps_idx,
+                         float *center, float *neighborhood, int32_t *idx, up3d_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UP3D_CHECK_ARG(B >= 0 && N > 0 && G >= 0 && K > 0, "up3d_subsample_group: bad sizes B=%d N=%d G=%d K=%d", B, N, G, K);
+    if (B == 0 || G == 0) return 0;
+    UP3D_CHECK_ARG(xyz && fps_idx && center && neighborhood, "up3d_subsample_group: null pointer");
+    UP3D_CHECK_ARG(K <= 1024, "up3d_subsample_group: K > 1024 not supported");
+    volatile float r2 = radius * radius;
+    ball_query_kernel<true><<<dim3(div_up(G, BQ_WARPS), B), BQ_WARPS * 32, sizeof(int32_t) * BQ_WARPS * K, stream>>>(
+        N, G, K, r2, nullptr, xyz, fps_idx, idx, center, neighborhood);
+    UP3D_LAUNCH_OK("ball_query_kernel<fused>");
+    return 0;
+}
+
+int up3d_group_points(int B, int C, int N, int M, int K, const float *points, const int32_t *idx, float *out,
+                      up3d_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UP3D_CHECK_ARG(B >= 0 && C >= 0 && N > 0 && M >= 0 && K >= 0, "up3d_group_points: bad sizes");
+    if (B == 0 || C == 0 || M * K == 0) return 0;
+    UP3D_CHECK_ARG(points && idx && out, "up3d_group_points: null pointer");
+    UP3D_CHECK_ARG(C <= 65535 && B <= 65535, "up3d_group_points: B and C must be <= 65535");
+    group_points_kernel<<<dim3(div_up(M * K, 256), C, B), 256, 0, stream>>>(C, N, M, K, points, idx, out);
+    UP3D_LAUNCH_OK("group_points_kernel");
+    return 0;
+}
+
+int up3d_group_points_grad(int B, int C, int N, int M, int K, const float *grad_out, const int32_t *idx,
+                           float *grad_points, up3d_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UP3D_CHECK_ARG(B >= 0 && C >= 0 && N > 0 && M >= 0 && K >= 0, "up3d_group_points_grad: bad sizes");
+    if (B == 0 || C == 0) return 0;
+    UP3D_CHECK_ARG(grad_points != nullptr, "up3d_group_points_grad: null pointer");
+    UP3D_CUDA_OK(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)B * C * N, stream));
+    if (M * K == 0) return 0;
+    UP3D_CHECK_ARG(grad_out && idx, "up3d_group_points_grad: null pointer");
+    UP3D_CHECK_ARG(C <= 65535 && B <= 65535, "up3d_group_points_grad: B and C must be <= 65535");
+    group_points_grad_kernel<<<dim3(div_up(M * K, 256), C, B), 256, 0, stream>>>(C, N, M, K, grad_out, idx, grad_points);
+    UP3D_LAUNCH_OK("group_points_grad_kernel");
+    return 0;
+}
+
+int up3d_gather_points(int B, int C, int N, int M, const float *points, const int32_t *idx, float *out,
+                       up3d_stream_t stream) {
+    return up3d_group_points(B, C, N, M, 1, points, idx, out, stream);
+}
+int up3d_gather_points_grad(int B, int C, int N, int M, const float *grad_out, const int32_t *idx, float *grad_points,
+                            up3d_stream_t stream) {
+    return up3d_group_points_grad(B, C, N, M, 1, grad_out, idx, grad_points, stream);
+}
+
+}  // extern "C"
