@@ -339,6 +339,12 @@ void up3d_oracle_bin(int P, int W, int H, const up3d_oracle_geom *g, uint64_t *k
     }
 }
 
+/* power = -0.5f*(co.x*dx*dx + co.z*dy*dy) - co.y*dx*dy, in the operation order nvcc gives that expression */
+static inline float gauss_power(const float *co, float dx, float dy) {
+    const float A = fmaf(co[0] * dx, dx, (co[2] * dy) * dy);
+    return fmaf(-0.5f, A, -((co[1] * dx) * dy));
+}
+
 /* ------------------------------------------------------------------ A.6 blend forward */
 void up3d_oracle_blend_forward(int W, int H, const float *bg, const up3d_oracle_geom *g, const uint32_t *point_list,
                                const uint32_t *ranges, float *out_color /*3*H*W*/, float *final_T /*H*W*/,
@@ -358,7 +364,7 @@ void up3d_oracle_blend_forward(int W, int H, const float *bg, const up3d_oracle_
                     const uint32_t id = point_list[j];
                     const float dx = g->xy[2 * id] - pfx, dy = g->xy[2 * id + 1] - pfy;
                     const float *co = g->conic_opacity + 4 * id;
-                    const float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                    const float power = gauss_power(co, dx, dy);
                     if (power > 0.0f) continue;
                     const float alpha = fminf(0.99f, co[3] * expf(power));
                     if (alpha < 1.0f / 255.0f) continue;
@@ -415,7 +421,7 @@ void up3d_oracle_blend_backward(int P, int W, int H, const float *bg, const up3d
                     const uint32_t id = point_list[j];
                     const float dx = g->xy[2 * id] - pfx, dy = g->xy[2 * id + 1] - pfy;
                     const float *co = g->conic_opacity + 4 * id;
-                    const float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                    const float power = gauss_power(co, dx, dy);
                     if (power > 0.0f) continue;
                     const float G = expf(power);
                     const float alpha = fminf(0.99f, co[3] * G);

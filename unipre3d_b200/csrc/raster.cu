@@ -331,7 +331,8 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_RPW = 8;                                  // rows (of 32 keys) per warp per tile
 constexpr int SORT_TILE = SORT_WARPS * SORT_RPW * 32;        // 8192 keys per tile
 constexpr int SORT_SMEM_MAX_KEYS = 12288;                    // 4 arrays * 4 B * 12288 = 192 KB
-constexpr int SORT_FIXED_SMEM = (SORT_WARPS * 256 + 256 + 256 + 8) * 4;
+constexpr int SORT_MISC = 16;                                 // [0] survivors, [1..8] scan warp totals
+constexpr int SORT_FIXED_SMEM = (SORT_WARPS * 256 + 256 + 256 + SORT_MISC) * 4;
 
 struct SortArgs {
     const int32_t *view_rec_start;
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) depth_sort_kernel(const SortA
     uint32_t *wcnt = (uint32_t *)smem_raw;            // [SORT_WARPS][256]
     uint32_t *hist = wcnt + SORT_WARPS * 256;         // [256]
     uint32_t *dbase = hist + 256;                     // [256]
-    uint32_t *misc = dbase + 256;                     // [8]
+    uint32_t *misc = dbase + 256;                     // [SORT_MISC]
     const int v = blockIdx.x;
     const int rec0 = a.view_rec_start[v];
     const int n = a.view_rec_start[v + 1] - rec0;
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) depth_sort_kernel(const SortA
     if (a.use_smem) {
         // capacity rounded to a multiple of 4 keys so every array stays 16-byte aligned
         const int cap = (n + 3) & ~3;
-        kA = misc + 8; kB = kA + cap; iA = (int32_t *)(kB + cap); iB = iA + cap;
+        kA = misc + SORT_MISC; kB = kA + cap; iA = (int32_t *)(kB + cap); iB = iA + cap;
     } else {
         kA = a.sc.kA + rec0; kB = a.sc.kB + rec0; iA = a.sc.iA + rec0; iB = a.sc.iB + rec0;
     }
@@ -479,6 +480,14 @@ __device__ __forceinline__ bool rect_covers(uint32_t rect, int tx, int ty) {
     return tx >= minx && tx < maxx && ty >= miny && ty < maxy;
 }
 
+// power = -0.5f * (co.x*dx*dx + co.z*dy*dy) - co.y*dx*dy with the operation order nvcc gives the upstream
+// expression (so the power > 0 / alpha < 1/255 skip decisions do not depend on this compiler's contraction
+// choices and agree with oracle/raster_oracle.c): A = fma(co.x*dx, dx, (co.z*dy)*dy); fma(-0.5, A, -((co.y*dx)*dy)).
+__device__ __forceinline__ float gauss_power(const float4 co, float dx, float dy) {
+    const float A = xfma(xmul(co.x, dx), dx, xmul(xmul(co.z, dy), dy));
+    return xfma(-0.5f, A, -xmul(xmul(co.y, dx), dy));
+}
+
 struct TileChunk {  // one 256-record chunk compacted to the entries covering this tile
     float2 xy[UP3D_TILE_PIX];
     float4 co[UP3D_TILE_PIX];
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_forward_kernel(const Blen
             const float2 xy = ch.xy[j];
             const float4 co = ch.co[j];
             const float dx = xy.x - pfx, dy = xy.y - pfy;
-            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+            const float power = gauss_power(co, dx, dy);
             if (power > 0.0f) continue;
             const float alpha = fminf(0.99f, co.w * expf(power));
             if (alpha < 1.0f / 255.0f) continue;
@@ -646,7 +655,7 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
                 const float2 xy = ch.xy[j];
                 const float4 co = ch.co[j];
                 const float dx = xy.x - pfx, dy = xy.y - pfy;
-                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                const float power = gauss_power(co, dx, dy);
                 active = !(power > 0.0f);
                 if (active) {
                     const float G = expf(power);
