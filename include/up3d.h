@@ -157,6 +157,13 @@ UP3D_API int up3d_raster_debug_state(const up3d_raster_desc *d, const void *stat
 UP3D_API int up3d_raster_debug_tile_lists(const up3d_raster_desc *d, const void *state, int32_t *tile_counts,
                                  const int32_t *tile_offsets, int32_t *tile_lists, up3d_stream_t stream);
 
+/* Per-kernel device timing for the benchmark's roofline leg: when enabled, forward/backward record CUDA events
+ * on the launching stream around each kernel (do not enable while capturing a CUDA graph).  read() blocks on the
+ * last event and returns milliseconds for [project, depth_sort, blend_forward, grad-clear, blend_backward,
+ * geometry_backward] of the most recent forward / backward on this host thread (-1 where not recorded). */
+UP3D_API int up3d_raster_timing_enable(int enable);
+UP3D_API int up3d_raster_timing_read(float *ms6);
+
 /* ------------------------------------------------------------------------------------------
  * Fused loss (train_network.py:260-302 + utils/loss_utils.py:23-45): focal-L2 between
  * rendered (V,3,H,W) and gt (V,3,H,W); writes the scalar mean loss (loss_out[0]) and

@@ -48,6 +48,8 @@ def _load() -> C.CDLL:
         "up3d_raster_debug_state": (i32, [D] + [vp] * 11),
         "up3d_raster_debug_tile_lists": (i32, [D] + [vp] * 5),
         "up3d_focal_l2_loss": (i32, [i64, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp]),
+        "up3d_raster_timing_enable": (i32, [i32]),
+        "up3d_raster_timing_read": (i32, [C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -60,7 +62,8 @@ lib = _load()
 EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_resident_points", "up3d_ball_query",
             "up3d_group_points", "up3d_group_points_grad", "up3d_gather_points", "up3d_gather_points_grad",
             "up3d_subsample_group", "up3d_raster_state_bytes", "up3d_raster_scratch_bytes", "up3d_raster_forward",
-            "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_focal_l2_loss"]
+            "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_focal_l2_loss",
+            "up3d_raster_timing_enable", "up3d_raster_timing_read"]
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0

@@ -979,6 +979,18 @@ static int validate_desc(const up3d_raster_desc *d) {
     return 0;
 }
 
+// Optional per-kernel timing with CUDA events recorded on the launching stream (bench.py's roofline leg).
+// Slots: 0 project, 1 depth_sort, 2 blend_forward, 3 gacc clear, 4 blend_backward, 5 geometry_backward.
+struct Timing {
+    bool enabled = false, created = false;
+    cudaEvent_t ev[8];
+    bool fwd_valid = false, bwd_valid = false;
+};
+static thread_local Timing g_timing;
+static inline void tick(int i, cudaStream_t s) {
+    if (g_timing.enabled) cudaEventRecord(g_timing.ev[i], s);
+}
+
 static ViewConst make_view_const(const up3d_raster_desc *d) {
     ViewConst vc;
     vc.W = d->width; vc.H = d->height;
@@ -1027,12 +1039,14 @@ int up3d_raster_forward(const up3d_raster_desc *d, const float *means3D, const f
     Scratch sc = carve_scratch(d, scratch);
     const ViewConst vc = make_view_const(d);
     const int V = d->n_views;
+    tick(0, stream);
     if (d->max_set_size > 0) {
         ProjectArgs pa{vc, means3D, shs, colors_precomp, opacities, scales, rotations, viewmats, projmats, campos,
                        d->set_offsets, d->view_set, d->view_rec_start, radii, st};
         project_kernel<<<dim3(div_up(d->max_set_size, 256), V), 256, 0, stream>>>(pa);
         UP3D_LAUNCH_OK("project_kernel");
     }
+    tick(1, stream);
     {
         SortArgs sa{d->view_rec_start, st, sc, d->max_set_size <= SORT_SMEM_MAX_KEYS ? 1 : 0};
         size_t smem = SORT_FIXED_SMEM;
@@ -1041,11 +1055,14 @@ int up3d_raster_forward(const up3d_raster_desc *d, const float *means3D, const f
         depth_sort_kernel<<<V, SORT_THREADS, smem, stream>>>(sa);
         UP3D_LAUNCH_OK("depth_sort_kernel");
     }
+    tick(2, stream);
     {
         BlendArgs ba{d->width, d->height, d->view_rec_start, bg, out_color, invdepth, st};
         blend_forward_kernel<<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, 0, stream>>>(ba);
         UP3D_LAUNCH_OK("blend_forward_kernel");
     }
+    tick(3, stream);
+    g_timing.fwd_valid = g_timing.enabled;
     return 0;
 }
 
@@ -1067,12 +1084,15 @@ int up3d_raster_backward(const up3d_raster_desc *d, const float *means3D, const 
     Scratch sc = carve_scratch(d, scratch);
     const ViewConst vc = make_view_const(d);
     const int V = d->n_views;
+    tick(4, stream);
     UP3D_CUDA_OK(cudaMemsetAsync(sc.gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)d->n_records, stream));
+    tick(5, stream);
     if (V > 0) {
         BlendBwdArgs ba{d->width, d->height, d->view_rec_start, bg, dL_dcolor, sc.gacc, st};
         blend_backward_kernel<<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, 0, stream>>>(ba);
         UP3D_LAUNCH_OK("blend_backward_kernel");
     }
+    tick(6, stream);
     GeomBwdArgs ga{vc, means3D, shs, colors_precomp, opacities, scales, rotations, viewmats, projmats, campos,
                    d->set_offsets, d->set_view_start, d->view_rec_start, sc.gacc, st,
                    dL_dmeans3D, dL_dmeans2D, dL_dshs, dL_dcolors, dL_dopacities, dL_dscales, dL_drotations};
@@ -1081,6 +1101,33 @@ int up3d_raster_backward(const up3d_raster_desc *d, const float *means3D, const 
         if (d->sh_coeffs <= 4 || d->sh_degree <= 1) geometry_backward_kernel<4><<<grid, 128, 0, stream>>>(ga);
         else geometry_backward_kernel<16><<<grid, 128, 0, stream>>>(ga);
         UP3D_LAUNCH_OK("geometry_backward_kernel");
+    }
+    tick(7, stream);
+    g_timing.bwd_valid = g_timing.enabled;
+    return 0;
+}
+
+int up3d_raster_timing_enable(int enable) {
+    if (enable && !g_timing.created) {
+        for (int i = 0; i < 8; ++i) UP3D_CUDA_OK(cudaEventCreate(&g_timing.ev[i]));
+        g_timing.created = true;
+    }
+    g_timing.enabled = enable != 0;
+    g_timing.fwd_valid = g_timing.bwd_valid = false;
+    return 0;
+}
+
+int up3d_raster_timing_read(float *ms6) {
+    UP3D_CHECK_ARG(ms6 != nullptr, "up3d_raster_timing_read: null output");
+    for (int i = 0; i < 6; ++i) ms6[i] = -1.f;
+    if (!g_timing.created) return 0;
+    if (g_timing.fwd_valid) {
+        UP3D_CUDA_OK(cudaEventSynchronize(g_timing.ev[3]));
+        for (int i = 0; i < 3; ++i) UP3D_CUDA_OK(cudaEventElapsedTime(&ms6[i], g_timing.ev[i], g_timing.ev[i + 1]));
+    }
+    if (g_timing.bwd_valid) {
+        UP3D_CUDA_OK(cudaEventSynchronize(g_timing.ev[7]));
+        for (int i = 0; i < 3; ++i) UP3D_CUDA_OK(cudaEventElapsedTime(&ms6[3 + i], g_timing.ev[4 + i], g_timing.ev[5 + i]));
     }
     return 0;
 }

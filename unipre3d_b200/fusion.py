@@ -1,0 +1,58 @@
+"""Object-level point/image feature fusion, restating /root/reference/fusion/feat_fusion.py:23-145 without host
+synchronisation.
+
+The reference compacts the in-image points with `torch.nonzero`, sizes its z-buffer from
+`unique_ids.max().item()` (a blocking D2H read every step) and scatters into a dense output.  Here the same
+arithmetic runs on fixed-size tensors: the z-buffer always has B*H*W cells, masked points carry +inf depth, and the
+final assignment is a masked gather.  Results are identical (same projection, same rounding, same (pixel_y*H +
+pixel_x) cell hash, same `image_features[b, :, pixel_x, pixel_y]` indexing quirk).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+
+class FeatureFusion:
+    def __init__(self, fusion_mlp: nn.Module):
+        self.fusion_mlp = fusion_mlp
+
+    @staticmethod
+    def project_points_to_image(center, c2w_matrix, intrinsic):
+        """feat_fusion.py:23-56.  c2w_matrix is the row-vector (transposed) camera-to-world 4x4."""
+        ones = torch.ones([*center.shape[:2], 1], device=center.device, dtype=center.dtype)
+        coords_h = torch.cat([center, ones], dim=2)
+        w2c = torch.linalg.inv(c2w_matrix.permute(0, 2, 1))
+        cam = torch.matmul(w2c, coords_h.transpose(1, 2)).transpose(1, 2)
+        px = (cam[..., 0] * float(intrinsic[0][0])) / cam[..., 2] + float(intrinsic[0][2])
+        py = (cam[..., 1] * float(intrinsic[1][1])) / cam[..., 2] + float(intrinsic[1][2])
+        return torch.round(torch.stack([px, py], -1)), cam[..., 2]
+
+    def __call__(self, x, center, image_features, c2w_projection_matrix, intrinsic):
+        B, N = center.shape[:2]
+        C, H, W = image_features.shape[1:]
+        if c2w_projection_matrix.dim() == 4:
+            c2w_projection_matrix = c2w_projection_matrix[:, 0]
+        with torch.no_grad():
+            pi_xy, p_depth = self.project_points_to_image(center, c2w_projection_matrix, intrinsic)
+            fx, fy = pi_xy[..., 0], pi_xy[..., 1]
+            # NaN-safe: comparisons with NaN are False, as in the reference after .long() of a finite value
+            inside = (fx >= 0) & (fy >= 0) & (fx < H) & (fy < W) & (p_depth >= 0)
+            ix = torch.where(inside, fx, torch.zeros_like(fx)).long()
+            iy = torch.where(inside, fy, torch.zeros_like(fy)).long()
+            cell = torch.arange(B, device=center.device).unsqueeze(1) * (H * W) + iy * H + ix       # (B,N)
+            depth_m = torch.where(inside, p_depth, torch.full_like(p_depth, float("inf")))
+            zbuf = torch.full((B * H * W + H * W,), float("inf"), device=center.device, dtype=p_depth.dtype)
+            zbuf.scatter_reduce_(0, cell.reshape(-1), depth_m.reshape(-1), reduce="amin", include_self=True)
+            keep = inside & (p_depth == zbuf[cell])
+            bidx = torch.arange(B, device=center.device).unsqueeze(1).expand(B, N)
+        mapped = image_features[bidx, :, ix, iy]                                                     # (B,N,C)
+        mapped = torch.where(keep.unsqueeze(-1), mapped, torch.zeros_like(mapped))
+        x_num = x.shape[1]
+        if x_num > N:  # transformer: CLS token gets zeros
+            x_patch = torch.cat([x[:, 1:], mapped], dim=-1)
+            cls = torch.cat([x[:, 0:1], torch.zeros((B, 1, C), device=center.device, dtype=x.dtype)], dim=-1)
+            x = torch.cat([cls, x_patch], dim=1)
+        else:
+            x = torch.cat([x, mapped], dim=-1)
+        return self.fusion_mlp(x)

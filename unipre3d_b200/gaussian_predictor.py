@@ -1,0 +1,187 @@
+"""GaussianSplatPredictor / PointFeaturePredictor with the reference's class names, constructor, forward
+signature, output dict and state-dict keys (/root/reference/model/gaussian_predictor.py:16-447,
+/root/reference/model/point_predictor.py:18-134).
+
+Scope: the object-level fusion path every shipped object config uses
+(`opt.use_fusion: true`, `opt.level: object`) with the `transformer` backbone.  Other backbones raise
+NotImplementedError naming the §8 row that would add them.
+
+Quirks reproduced on purpose (results must match the reference, SURVEY.md §7 "Quirk parity"):
+  * rotation_activation = F.normalize(x, dim=-1) is applied to the (B,4,P) tensor, i.e. it normalises over
+    the P points, not over the 4 quaternion components (gaussian_predictor.py:254,318);
+  * scaling = exp(clamp(x, -1, 20))  -> sigma >= e^-1 (252);
+  * `_forward_basic` of the reference calls a method that does not exist (98-110); the evident intent
+    (= `_process_network_output(..., is_scene_level=False)` on the fusion-less backbone) is implemented instead.
+
+Image branch: the reference runs a frozen SD-VAE (model/image_predictor.py:56-81, weights not shipped) under
+no_grad and feeds `decoder_block_3` (128 channels at image resolution) to the trainable `image_conv`.
+`FrozenImageStem` is a weight-free stand-in with the same interface and output shape.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .backbone import PointTransformerEncoder
+
+
+def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
+    return nn.init.trunc_normal_(tensor, mean=mean, std=std, a=a, b=b)
+
+
+class FrozenImageStem(nn.Module):
+    """Stand-in for ImageFeaturePredictor: frozen, gradient-free, returns {"decoder_block_3": (n,128,R,R)}."""
+
+    def __init__(self, cfg, out_channels):
+        super().__init__()
+        self.cfg, self.out_channels = cfg, out_channels
+        self.encoder_config = {"block_out_channels": [128, 256, 512, 512]}
+        g = torch.Generator().manual_seed(1234)
+        self.register_buffer("proj", torch.randn(128, 3, generator=g) * 0.7, persistent=False)
+        self.register_buffer("shift", torch.randn(128, generator=g) * 0.3, persistent=False)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        f = torch.einsum("oc,nchw->nohw", self.proj, x.float()) + self.shift.view(1, -1, 1, 1)
+        return {"decoder_block_3": torch.sin(f)}
+
+
+class PointFeaturePredictor(nn.Module):
+    """point_predictor.py:18-134: backbone + `final` MLP (-> 23 channels)."""
+
+    def __init__(self, cfg, out_channels, pretrained_path=None):
+        super().__init__()
+        self.cfg, self.out_channels = cfg, out_channels
+        model_type = cfg.model.backbone_type.lower()
+        if model_type == "transformer":
+            self.encoder = PointTransformerEncoder(in_channels=3, num_groups=128, encoder_dims=384, depth=16,
+                                                   use_fusion=bool(getattr(cfg.opt, "use_fusion", True)))
+            self.final = nn.Sequential(nn.Linear(384, 128), nn.ReLU(), nn.Linear(128, 23))
+        else:
+            raise NotImplementedError(
+                f"backbone_type={model_type!r}: only 'transformer' (SURVEY.md §8a rows B1-B5) is built; "
+                "pointmlp is row B6, ptv3/sparseunet rows P1/P2 (need spconv), pcm/mamba3d are out of scope")
+        if pretrained_path is not None:
+            info = self.load_state_dict(torch.load(pretrained_path), strict=False)
+            print(f"Loaded pretrained weights from {pretrained_path}")
+            print(f"Missing keys: {info.missing_keys}")
+            print(f"Unexpected keys: {info.unexpected_keys}")
+
+    def forward(self, x):
+        x, center = self.encoder(x, None, None, None, None)
+        return self.final(x).permute(0, 2, 1), center
+
+    def forward_feat_fusion(self, x, image_features, c2w_projection_matrix, fusion_mlps, intrinsic):
+        x, center = self.encoder.forward(x, image_features, c2w_projection_matrix, fusion_mlps, intrinsic)
+        return self.final(x).permute(0, 2, 1), center
+
+
+class GaussianSplatPredictor(nn.Module):
+    MODEL_CONFIGS = {
+        "pointmlp": {"feature_dim": 128, "fusion_dim": 128, "final_dim": 128},
+        "transformer": {"feature_dim": 384, "fusion_dim": 384, "final_dim": 384},
+        "sparseunet": {"feature_dim": 128, "fusion_dim": 32, "final_dim": 32},
+        "ptv3": {"feature_dim": 32, "fusion_dim": 32, "final_dim": 32},
+    }
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.use_fusion = hasattr(cfg.opt, "use_fusion") and cfg.opt.use_fusion
+        self.split_dimensions = [3, 1, 3, 4, 3]
+        if cfg.model.max_sh_degree != 0:
+            self.split_dimensions.append(((cfg.model.max_sh_degree + 1) ** 2 - 1) * 3)
+        if cfg.opt.level != "object":
+            raise NotImplementedError("opt.level='scene' (SURVEY.md §8a rows P1/P2) needs the sparse-conv backbones")
+        pretrained = getattr(cfg.opt, "pretrained_ckpt", None)
+        if self.use_fusion:
+            self.image_network = FrozenImageStem(cfg, [128])
+            self.point_network = PointFeaturePredictor(cfg, self.split_dimensions, pretrained_path=pretrained)
+            mc = self.MODEL_CONFIGS[cfg.model.backbone_type]
+            in_dim = self.image_network.encoder_config["block_out_channels"][0]
+            self.image_conv = nn.Sequential(nn.GroupNorm(32, in_dim, eps=1e-06),
+                                            nn.Conv2d(in_dim, mc["feature_dim"], kernel_size=1))
+            self.fusion_mlps = nn.Sequential(nn.Linear(mc["feature_dim"] + mc["fusion_dim"], mc["fusion_dim"]),
+                                             nn.ReLU())
+            self.intrinsic = self._get_camera_intrinsics()
+        else:
+            self.point_network = PointFeaturePredictor(cfg, self.split_dimensions, pretrained_path=pretrained)
+        if cfg.model.max_sh_degree > 0:
+            v_to_sh = torch.tensor([[0, 0, -1], [-1, 0, 0], [0, 1, 0]], dtype=torch.float32)
+            self.register_buffer("sh_to_v_transform", v_to_sh.transpose(0, 1).unsqueeze(0))
+            self.register_buffer("v_to_sh_transform", v_to_sh.unsqueeze(0))
+
+    # -- activations (gaussian_predictor.py:249-254)
+    pos_act = staticmethod(torch.tanh)
+    opacity_activation = staticmethod(torch.sigmoid)
+
+    @staticmethod
+    def scaling_activation(x):
+        return torch.exp(torch.clamp(x, -1, 20))
+
+    @staticmethod
+    def rotation_activation(x):
+        return torch.nn.functional.normalize(x, dim=-1, eps=1e-6)
+
+    def _get_camera_intrinsics(self):
+        fov, res = self.cfg.data.fov, self.cfg.data.training_resolution
+        K = np.zeros((3, 4))
+        K[2, 2] = 1
+        focal = (res / 2.0) / math.tan(math.radians(fov / 2.0))
+        K[0, 0] = K[1, 1] = focal
+        K[0, 2] = K[1, 2] = res / 2.0
+        return K
+
+    def forward(self, point_cloud, image: Optional[torch.Tensor] = None,
+                source_cameras_view_to_world: Optional[torch.Tensor] = None,
+                unprojected_coords: Optional[torch.Tensor] = None, links: Optional[torch.Tensor] = None):
+        if self.use_fusion:
+            return self._forward_fusion(point_cloud, image, source_cameras_view_to_world, unprojected_coords)
+        return self._forward_basic(point_cloud, source_cameras_view_to_world)
+
+    def _forward_basic(self, point_cloud, source_cameras_view_to_world):
+        point_output, center = self.point_network(point_cloud)
+        out = self._process_network_output(point_output.split(self.split_dimensions, dim=1), center)
+        return {k: v.contiguous() for k, v in out.items()}
+
+    def _forward_fusion(self, point_cloud, image, source_cameras_view_to_world=None, unprojected_coords=None):
+        B, N_views = image.shape[0], image.shape[1]
+        image = image.reshape(B * N_views, *image.shape[2:])
+        image_output = self.image_network.forward(image)
+        image_features = self.image_conv.forward(image_output["decoder_block_3"])
+        point_features, center = self.point_network.forward_feat_fusion(
+            point_cloud, image_features, source_cameras_view_to_world, self.fusion_mlps, self.intrinsic)
+        out = self._process_network_output(point_features.split(self.split_dimensions, dim=1), center)
+        out = {k: v.reshape(B, N_views * v.shape[1], *v.shape[2:]) for k, v in out.items()}   # _multi_view_union
+        return {k: v.contiguous() for k, v in out.items()}
+
+    @staticmethod
+    def _flatten_vector(x):
+        return x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+
+    def _process_network_output(self, network_output: List[torch.Tensor], center) -> Dict[str, torch.Tensor]:
+        """Object branch of gaussian_predictor.py:279-328."""
+        xyz_raw, opacity, scaling, rotation, features_dc = network_output[:5]
+        pos = self.pos_act(xyz_raw) * self.cfg.model.offset_scale
+        pos = pos.permute(0, 2, 1) + center[:, :, :3]
+        if self.cfg.model.isotropic:
+            scaling = scaling[:, :1].expand(-1, 3, -1)
+        out = {
+            "xyz": pos,
+            "opacity": self._flatten_vector(self.opacity_activation(opacity)),
+            "scaling": self._flatten_vector(self.scaling_activation(scaling)),
+            "rotation": self._flatten_vector(self.rotation_activation(rotation)),
+            "features_dc": self._flatten_vector(features_dc).unsqueeze(2),
+        }
+        if self.cfg.model.max_sh_degree > 0:
+            rest = self._flatten_vector(network_output[5])
+            out["features_rest"] = rest.reshape(*rest.shape[:2], -1, 3)
+        else:
+            dc = out["features_dc"]
+            out["features_rest"] = torch.zeros((dc.shape[0], (self.cfg.model.max_sh_degree + 1) ** 2 - 1, 3),
+                                               dtype=dc.dtype, device=dc.device)
+        return out

@@ -1,0 +1,79 @@
+"""Synthetic ShapeNet-shaped batches (SURVEY.md §8d "synthetic inputs"): the dict the reference's ShapeNet
+loader emits (/root/reference/dataset/shapenet.py:630-661, 530-535) without any dataset on disk.
+
+Per sample: V = data.input_images + opt.imgs_per_obj views (shapenet.py:609-612), cameras on a sphere of radius
+1.75 looking at the origin (shapenet.py:674-764), projection from znear/zfar/fov, all matrices transposed
+(row-vector convention, shapenet.py:303-316); cloud = N points in a ball, mean-centred, max radius 0.5
+(shapenet.py:480-492); GT images = U[0,1] inside a random disc on the exact background colour elsewhere
+(so focal_l2 exercises both weights).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+
+from . import camera as cam
+
+CAMERA_DISTANCE = 1.75
+
+
+def camera_pool(cfg, num: int = 24):
+    """`num` poses: azimuth sweep, first half elevation 0-20 deg, second half 20-90 deg (shapenet.py:747-764)."""
+    fov = math.radians(cfg.data.fov)
+    proj = cam.get_projection_matrix(cfg.data.znear, cfg.data.zfar, fov, fov)
+    half = num // 2
+    az = np.linspace(-180, 180, half)
+    poses = list(zip(az, np.linspace(0, 20, half))) + list(zip(az, np.linspace(20, 88, num - half)))
+    return [cam.make_view(*cam.look_at_pose(a, e, CAMERA_DISTANCE), proj) for a, e in poses]
+
+
+def make_cloud(n_points: int, rng: np.random.Generator, in_channels: int = 3) -> np.ndarray:
+    d = rng.normal(size=(n_points, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p = d * rng.uniform(0, 1, (n_points, 1)) ** (1.0 / 3.0)
+    p = p - p.mean(0, keepdims=True)
+    p = p / np.linalg.norm(p, axis=1).max() * 0.5
+    if in_channels == 4:  # height channel (shapenet.py:424-429)
+        p = np.concatenate([p, p[:, 2:3] - p[:, 2:3].min()], 1)
+    return p.astype(np.float32)
+
+
+def make_batch(cfg, batch_size: int, n_points: int, seed: int = 0, pin: bool = False) -> Dict[str, torch.Tensor]:
+    rng = np.random.default_rng(seed)
+    V = int(cfg.data.input_images) + int(cfg.opt.imgs_per_obj)
+    R = int(cfg.data.training_resolution)
+    pool = camera_pool(cfg)
+    bgc = 1.0 if cfg.data.white_background else 0.0
+    keys = ("world_view_transform", "view_to_world_transform", "full_proj_transform", "camera_center")
+    out = {k + "s": [] for k in keys}
+    clouds, gts = [], []
+    yy, xx = np.mgrid[0:R, 0:R]
+    for _ in range(batch_size):
+        sel = rng.permutation(len(pool))[:V]
+        for k in keys:
+            out[k + "s"].append(torch.stack([pool[i][k] for i in sel]))
+        clouds.append(make_cloud(n_points, rng, int(cfg.model.in_channels)))
+        cx, cy, rad = rng.uniform(0.35 * R, 0.65 * R), rng.uniform(0.35 * R, 0.65 * R), rng.uniform(0.2 * R, 0.4 * R)
+        disc = ((xx - cx) ** 2 + (yy - cy) ** 2) <= rad ** 2
+        img = rng.uniform(0, 1, (V, 3, R, R)).astype(np.float32)
+        gts.append(np.where(disc[None, None], img, np.float32(bgc)))
+    batch = {k: torch.stack(v).float() for k, v in out.items()}
+    batch["gt_images"] = torch.from_numpy(np.stack(gts))
+    batch["point_cloud"] = {"pos": torch.from_numpy(np.stack(clouds))}
+    if pin and torch.cuda.is_available():
+        batch = {k: ({kk: vv.pin_memory() for kk, vv in v.items()} if isinstance(v, dict) else v.pin_memory())
+                 for k, v in batch.items()}
+    return batch
+
+
+def batch_nbytes(batch) -> int:
+    n = 0
+    for v in batch.values():
+        if isinstance(v, dict):
+            n += sum(t.numel() * t.element_size() for t in v.values())
+        else:
+            n += v.numel() * v.element_size()
+    return n

@@ -1,0 +1,269 @@
+"""Pre-training step of the render-loss path with the reference trainer's shape
+(/root/reference/train_network.py:136-220 ModelManager, 222-302 ValidationManager, 305-464 Trainer) on B200.
+
+What changes relative to the reference loop (same math, fewer host round trips):
+  * `render_validation_views` renders all B*V' (object, view) pairs in ONE batched launch set
+    (gaussian_renderer.render_batch_predicted) instead of a Python double loop of render calls (418-442);
+  * `focal_l2_loss` value + gradient come from one fused kernel;
+  * `_check_and_clip_gradients` (368-390): the per-parameter `.any()` host syncs become one device-side
+    total-norm; the "skip the step on NaN/Inf" rule is applied on the device through fused AdamW's `found_inf`
+    hook, so the optimizer state is untouched on a bad step exactly as in the reference (336-340);
+  * the whole step (forward, render, loss, backward, clip, AdamW) can be captured into ONE CUDA graph
+    (`use_cuda_graph=True`), replayed per iteration with inputs copied into static buffers;
+  * multi-GPU: one process per GPU, objects sharded over ranks (train_network.py:95-103 semantics), gradients
+    all-reduced with NCCL (torch DDP buckets overlap the backward; SyncBatchNorm as train_network.py:183).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .gaussian_predictor import GaussianSplatPredictor
+from .gaussian_renderer import render_batch_predicted
+from .loss import focal_l2_loss, l1_loss, l2_loss
+
+
+def _to_device(x, device, non_blocking=True):
+    if isinstance(x, dict):
+        return {k: _to_device(v, device, non_blocking) for k, v in x.items()}
+    if torch.is_tensor(x):
+        return x.to(device, non_blocking=non_blocking)
+    return x
+
+
+def prepare_model_inputs(data, cfg, bs_per_gpu, device):
+    """utils/general_utils.py:251-293 (object level)."""
+    point_cloud = data["point_cloud"] if "point_cloud" in data else data
+    inputs = {"point_cloud": point_cloud,
+              "source_cameras_view_to_world": data["view_to_world_transforms"][:, : cfg.data.input_images, ...],
+              "image": None, "unprojected_coords": None}
+    if cfg.opt.use_fusion:
+        inputs["image"] = data["gt_images"][:, : cfg.data.input_images, ...]
+    return _to_device(inputs, device)
+
+
+class EMA:
+    """Exponential moving average of the model weights with ema_pytorch's default schedule (the reference
+    wraps the model in ema_pytorch.EMA(beta, update_every, update_after_step), train_network.py:188-198):
+    copy weights until `update_after_step`, then every `update_every` steps
+    ema = lerp(ema, w, 1 - decay), decay = clamp(1 - (1 + t)^(-2/3), 0, beta), t = step - update_after_step - 1."""
+
+    def __init__(self, model, beta=0.9999, update_every=10, update_after_step=100, inv_gamma=1.0, power=2.0 / 3.0):
+        self.online = model
+        self.ema_model = copy.deepcopy(model).requires_grad_(False).eval()
+        self.beta, self.update_every, self.update_after_step = beta, update_every, update_after_step
+        self.inv_gamma, self.power = inv_gamma, power
+        self.step, self.initted = 0, False
+
+    def _pairs(self):
+        src = self.online.module if hasattr(self.online, "module") else self.online
+        fl = lambda m: [p for p in list(m.parameters()) + list(m.buffers()) if p.dtype.is_floating_point]
+        return fl(self.ema_model), fl(src)
+
+    def current_decay(self) -> float:
+        epoch = max(self.step - self.update_after_step - 1, 0)
+        if epoch <= 0:
+            return 0.0
+        return min(max(1 - (1 + epoch / self.inv_gamma) ** -self.power, 0.0), self.beta)
+
+    @torch.no_grad()
+    def update(self):
+        step = self.step
+        self.step += 1
+        if step % self.update_every != 0:
+            return
+        e, s = self._pairs()
+        if step <= self.update_after_step or not self.initted:
+            torch._foreach_copy_(e, s)
+            self.initted = True
+            return
+        torch._foreach_lerp_(e, s, 1.0 - self.current_decay())
+
+
+class ModelManager:
+    """train_network.py:136-220."""
+
+    def __init__(self, cfg, device, capturable: bool = False):
+        self.cfg, self.device = cfg, device
+        self.model = GaussianSplatPredictor(cfg).to(device)
+        base_lr = cfg.opt.base_lr
+        groups = [{"params": list(self.model.point_network.parameters()), "lr": base_lr}]
+        if cfg.opt.use_fusion:
+            groups += [{"params": list(self.model.fusion_mlps.parameters()), "lr": base_lr},
+                       {"params": list(self.model.image_conv.parameters()), "lr": base_lr}]
+        if capturable:  # tensor learning rates so a captured graph sees StepLR updates
+            for g in groups:
+                g["lr"] = torch.tensor(float(g["lr"]), device=device)
+        self.optimizer = torch.optim.AdamW(groups, lr=0.0 if not capturable else torch.tensor(0.0, device=device),
+                                           eps=1e-15, betas=tuple(cfg.opt.betas), fused=True, capturable=capturable)
+        self.step_lr, self.lr_gamma, self._sched_step = cfg.opt.step_lr, cfg.opt.lr_gamma, 0
+        self.ddp = None
+        if cfg.general.multiple_gpu and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.model)
+            self.ddp = torch.nn.parallel.DistributedDataParallel(
+                self.model, device_ids=[device.index], output_device=device.index, broadcast_buffers=False,
+                find_unused_parameters=False, gradient_as_bucket_view=True, bucket_cap_mb=64)
+        self.ema = EMA(self.model, beta=cfg.opt.ema.beta, update_every=cfg.opt.ema.update_every,
+                       update_after_step=cfg.opt.ema.update_after_step) if cfg.opt.ema.use else None
+
+    @property
+    def forward_model(self):
+        return self.ddp if self.ddp is not None else self.model
+
+    def scheduler_step(self):
+        """StepLR(step_size=opt.step_lr, gamma=opt.lr_gamma) (train_network.py:160-163), in place."""
+        if self.step_lr == -1:
+            return
+        self._sched_step += 1
+        if self._sched_step % self.step_lr == 0:
+            for g in self.optimizer.param_groups:
+                if torch.is_tensor(g["lr"]):
+                    g["lr"].mul_(self.lr_gamma)
+                else:
+                    g["lr"] = g["lr"] * self.lr_gamma
+
+    def save_checkpoint(self, iteration: int, best_psnr: float, save_path: str) -> None:
+        """Same dict keys as train_network.py:200-210."""
+        torch.save({"iteration": iteration, "optimizer_state_dict": self.optimizer.state_dict(),
+                    "model_state_dict": (self.ema.ema_model.state_dict() if self.ema else self.model.state_dict()),
+                    "best_PSNR": best_psnr}, save_path)
+
+
+class ValidationManager:
+    def __init__(self, cfg, device):
+        self.cfg, self.device = cfg, device
+        self.background = torch.tensor([1, 1, 1] if cfg.data.white_background else [0, 0, 0], dtype=torch.float32,
+                                       device=device)
+
+    def calculate_losses(self, rendered_images, gt_images, iteration: int) -> Dict[str, torch.Tensor]:
+        """train_network.py:260-302.  LPIPS-VGG (after opt.start_lpips_after) needs pretrained VGG weights that
+        are not available offline; it is outside the measured path."""
+        losses = {}
+        if self.cfg.opt.loss == "focal_l2":
+            losses["l12_loss"] = focal_l2_loss(rendered_images, gt_images, self.background,
+                                               self.cfg.opt.non_bg_color_loss_rate, self.cfg.opt.bg_color_loss_rate)
+        else:
+            losses["l12_loss"] = (l1_loss if self.cfg.opt.loss == "l1" else l2_loss)(rendered_images, gt_images)
+        if self.cfg.opt.lambda_lpips != 0 and iteration > self.cfg.opt.start_lpips_after:
+            raise NotImplementedError("LPIPS loss needs VGG weights (not shipped); set opt.lambda_lpips=0")
+        losses["total_loss"] = losses["l12_loss"]
+        return losses
+
+
+class Trainer:
+    """Step driver.  `train_iteration(data)` == reference 450-464 + 333-352 for one batch dict (host tensors)."""
+
+    def __init__(self, cfg, device: Optional[torch.device] = None, use_cuda_graph: bool = False,
+                 autocast_dtype: Optional[torch.dtype] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("unipre3d_b200.Trainer needs a CUDA device (there is no CPU fallback)")
+        self.cfg = cfg
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        torch.manual_seed(cfg.general.random_seed)
+        torch.cuda.manual_seed_all(cfg.general.random_seed)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.bs_per_gpu = cfg.opt.batch_size if self.world == 1 else cfg.opt.batch_size // self.world
+        self.use_cuda_graph = use_cuda_graph
+        self.autocast_dtype = autocast_dtype
+        self.model_manager = ModelManager(cfg, self.device, capturable=use_cuda_graph)
+        self.validation_manager = ValidationManager(cfg, self.device)
+        self.params = [p for p in self.model_manager.model.parameters() if p.requires_grad]
+        self.found_inf = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.model_manager.optimizer.grad_scale = None
+        self.model_manager.optimizer.found_inf = self.found_inf
+        self.iteration = 0
+        self._graph = None
+        self._static: Optional[dict] = None
+        self._loss_buf = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    # ---------------------------------------------------------------------------------------------
+    def render_validation_views(self, gaussian_splats, data) -> Tuple[torch.Tensor, torch.Tensor]:
+        """train_network.py:392-448, batched: views [input_images:] of every object in one call."""
+        bg = self.validation_manager.background
+        sl = slice(int(self.cfg.data.input_images), None)
+        out = render_batch_predicted(gaussian_splats, data["world_view_transforms"], data["full_proj_transforms"],
+                                     data["camera_centers"], bg, self.cfg, view_slice=sl)
+        rendered = out["render"]
+        gt = data["gt_images"][:, sl]
+        return rendered.reshape(-1, *rendered.shape[2:]), gt.reshape(-1, *gt.shape[2:])
+
+    def _forward_backward(self, data) -> torch.Tensor:
+        mm = self.model_manager
+        model_inputs = prepare_model_inputs(data, self.cfg, self.bs_per_gpu, self.device)
+        mm.forward_model.train()
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                splats = mm.forward_model(**model_inputs)
+            splats = {k: v.float() for k, v in splats.items()}
+        else:
+            splats = mm.forward_model(**model_inputs)
+        rendered, gt = self.render_validation_views(splats, data)
+        loss = self.validation_manager.calculate_losses(rendered, gt, self.iteration)["total_loss"]
+        loss.backward()
+        return loss.detach()
+
+    def _clip_and_step(self) -> None:
+        """368-390 + 343-344: total norm on the device; non-finite -> found_inf=1 -> fused AdamW leaves
+        parameters and moments untouched; else grads are scaled to max_norm 1.0."""
+        mm = self.model_manager
+        grads = [p.grad for p in self.params if p.grad is not None]
+        norms = torch._foreach_norm(grads, 2.0)
+        total = torch.linalg.vector_norm(torch.stack(norms), 2.0)
+        self.found_inf.copy_((~torch.isfinite(total)).float())
+        coef = torch.clamp(1.0 / (total + 1e-6), max=1.0)
+        coef = torch.where(torch.isfinite(coef), coef, torch.zeros_like(coef))
+        torch._foreach_mul_(grads, coef)
+        mm.optimizer.step()
+        mm.optimizer.zero_grad(set_to_none=False)
+
+    def _step_body(self, data) -> torch.Tensor:
+        loss = self._forward_backward(data)
+        self._clip_and_step()
+        return loss
+
+    # ---------------------------------------------------------------------------------------------
+    def _copy_into_static(self, data) -> None:
+        def cp(dst, src):
+            if isinstance(dst, dict):
+                for k in dst:
+                    cp(dst[k], src[k])
+            else:
+                dst.copy_(src, non_blocking=True)
+        cp(self._static, data)
+
+    def train_iteration(self, data, read_loss: bool = True):
+        """One optimisation step on a host (ideally pinned) batch dict.  Returns the loss (float) when
+        `read_loss` (a D2H read, as the reference's logging does) else the device scalar."""
+        self.iteration += 1
+        mm = self.model_manager
+        if not self.use_cuda_graph:
+            loss = self._step_body(_to_device(data, self.device))
+        else:
+            if self._static is None:
+                self._static = _to_device(data, self.device, non_blocking=False)
+                # warm-up on a side stream (allocator, cuBLAS handles, layout cache, lazy grads), then capture
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    for _ in range(3):
+                        self._step_body(self._static)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._loss_buf.copy_(self._step_body(self._static))
+            self._copy_into_static(data)
+            self._graph.replay()
+            loss = self._loss_buf
+        mm.scheduler_step()
+        if mm.ema:
+            mm.ema.update()
+        if read_loss:
+            self._loss_host.copy_(loss, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(self._loss_host)
+        return loss
