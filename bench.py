@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- views/sec of the UniPre3D render-loss pre-training step on B200.
+
+Workload (BASELINE.json configs[1]): transformer_pretraining, 8 objects x 4 rendered views per GPU, 8192-point
+clouds, 256x256 renders, synthetic ShapeNet-shaped batches, random-init weights.  One "step" = backbone forward ->
+GaussianSplatPredictor -> 32 renders -> focal-L2 -> backward -> grad clip -> AdamW (-> NCCL all-reduce when N > 1).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched through torch.distributed.run)
+  python bench.py --impl reference ...                       CPU port of the same step on the host cores (rank 0 only)
+
+One JSON line on rank 0.  `value`: inputs resident in HBM.  `e2e`: same step through Trainer.train_iteration with
+pinned HOST batches (H2D inside the timed region) and a D2H read of the loss every step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OBJECTS_PER_GPU, N_POINTS, RES = 8, 8192, 256
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_cfg(n_gpus: int):
+    from unipre3d_b200.config import compose
+    ov = [f"data.training_resolution={RES}", f"opt.batch_size={OBJECTS_PER_GPU * n_gpus}"]
+    if n_gpus > 1:
+        ov.append("general.device=[" + ",".join(str(i) for i in range(n_gpus)) + "]")
+    return compose(overrides=ov)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_cpu_port(args, as_reference: bool, budget_s: float = 25.0):
+    """CPU port (oracle/) on a bounded sample of the same workload: 1 object (8192 pts, 4 views 256x256) per step."""
+    from oracle import oracle_lib
+    from oracle.cpu_step import CpuStepper
+    from unipre3d_b200 import synthetic
+    cfg = make_cfg(1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    stepper = CpuStepper(cfg)
+    data = synthetic.make_batch(cfg, 1, N_POINTS, seed=0)
+    views = int(cfg.opt.imgs_per_obj)
+    steps, warm = (args.steps, args.warmup) if as_reference else (3, 1)
+    t0 = time.perf_counter()
+    for _ in range(warm):
+        stepper.step(data)
+    per = (time.perf_counter() - t0) / max(warm, 1)
+    if as_reference:
+        steps = max(1, min(steps, int(180.0 / max(per, 1e-3))))      # whole run within a few minutes
+    else:
+        steps = max(1, min(steps, int(budget_s / max(per, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        stepper.step(data)
+    dt = (time.perf_counter() - t0) / steps
+    cores = max(torch.get_num_threads(), oracle_lib.num_threads())
+    return {"value": views / dt, "unit": "views/s", "cores": cores, "kind": "port",
+            "sample": f"1 of {OBJECTS_PER_GPU} objects per step (8192 pts -> 128 Gaussians, {views} views 256x256), "
+                      f"{steps} timed steps after {warm} warm-up, torch CPU backbone + C/OpenMP rasterizer oracle",
+            "ms_per_step": dt * 1e3, "steps": steps, "warmup": warm}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = run_cpu_port(args, as_reference=True)
+    line = {"impl": "reference", "metric": "views/sec (8192 pts->256^2 render), full pre-training step",
+            "value": cb["value"], "unit": "views/s", "n_gpus": args.gpus, "steps": cb["steps"], "warmup": cb["warmup"],
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "transformer_pretraining, 8 objects x 4 views, 8192 pts, 256x256 (bounded sample: "
+                                   "1 object x 4 views per step)", "l2": "n/a (CPU)"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def raster_roofline(trainer, batch_dev, cfg, reps: int, peaks, peak_kind):
+    """Per-kernel device time of the rasterizer on the step's own Gaussians (CUDA events recorded by the C ABI on the
+    launching stream), and the HBM roofline of the dominant raster kernel."""
+    from unipre3d_b200 import _lib
+    from unipre3d_b200.trainer import prepare_model_inputs
+    model = trainer.model_manager.model
+    ms = np.zeros((reps, 6))
+    _lib.check(_lib.lib.up3d_raster_timing_enable(1))
+    buf = (C.c_float * 6)()
+    try:
+        for r in range(reps):
+            model.train()
+            splats = model(**prepare_model_inputs(batch_dev, cfg, OBJECTS_PER_GPU, trainer.device))
+            rendered, gt = trainer.render_validation_views(splats, batch_dev)
+            loss = trainer.validation_manager.calculate_losses(rendered, gt, 0)["total_loss"]
+            loss.backward()
+            _lib.check(_lib.lib.up3d_raster_timing_read(buf))
+            ms[r] = list(buf)
+            for p in trainer.params:
+                p.grad = None
+    finally:
+        _lib.check(_lib.lib.up3d_raster_timing_enable(0))
+    names = ["project", "depth_sort", "blend_forward", "grad_clear", "blend_backward", "geometry_backward"]
+    mean = ms.mean(0)
+    V = OBJECTS_PER_GPU * int(cfg.opt.imgs_per_obj)
+    P, HW, M = int(splats["xyz"].shape[1]), RES * RES, 4
+    # algorithmic bytes of blend_backward per launch (DESIGN.md "Kernels"): depth-ordered records read once per view
+    # (48 B each), per-pixel final_T / n_contrib / dL_dcolor (20 B), per-record 9-float partials read-modify-write
+    bwd_bytes = V * (P * 48 + HW * 20 + P * 9 * 4 * 2)
+    dom = "blend_backward"
+    t_dom = mean[names.index(dom)] * 1e-3
+    achieved = bwd_bytes / t_dom / 1e9 if t_dom > 0 else None
+    # traffic the reference's algorithm moves for the same views: P(240+36M) + 108 I + 40 WH per view
+    I = P * (HW // 256)
+    ref_bytes = V * (P * (240 + 36 * M) + 108 * I + 40 * HW)
+    raster_ms = float(mean.sum())
+    return {
+        "roofline": {"bound": "hbm", "kernel": "up3d::blend_backward_kernel", "achieved": achieved,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
+                     "traffic": None, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_launch": bwd_bytes, "launch_ms": float(mean[names.index(dom)])},
+        "raster_kernels_ms": {n: float(v) for n, v in zip(names, mean)},
+        "raster_stage": {"ms_per_step": raster_ms, "views_per_s": V / (raster_ms * 1e-3) if raster_ms > 0 else None,
+                         "reference_algorithm_bytes_per_step": ref_bytes,
+                         "effective_GBs_vs_reference_traffic": ref_bytes / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else None},
+    }
+
+
+def raster_only_headline(device, reps: int, peaks):
+    """Raster stage alone at the headline Gaussian count (P = 8192 per object, the pointMLP-true case of SURVEY §8d)."""
+    from unipre3d_b200 import _lib
+    from unipre3d_b200.rasterizer import rasterize_batch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests.helpers import make_camera, make_gaussians
+    B, V, P = OBJECTS_PER_GPU, 4, 8192
+    gs = [make_gaussians(P, seed=100 + i, regime="reference") for i in range(B)]
+    cat = {k: torch.tensor(np.concatenate([g[k] for g in gs], 0), device=device).requires_grad_(True) for k in gs[0]}
+    cams = [make_camera(az=360.0 * i / (B * V), el=5 + 2.0 * i) for i in range(B * V)]
+    vm = torch.tensor(np.stack([c["view"] for c in cams]), device=device)
+    pm = torch.tensor(np.stack([c["proj"] for c in cams]), device=device)
+    cp = torch.tensor(np.stack([c["campos"] for c in cams]), device=device)
+    bg = torch.zeros(3, device=device)
+    w = torch.randn(B * V, 3, RES, RES, device=device)
+    kw = dict(set_sizes=[P] * B, views_per_set=[V] * B, image_height=RES, image_width=RES, tanfovx=cams[0]["tanfovx"],
+              tanfovy=cams[0]["tanfovy"], sh_degree=1, shs=cat["shs"], invdepth=False)
+    buf = (C.c_float * 6)()
+    ms = np.zeros((reps, 6))
+    _lib.check(_lib.lib.up3d_raster_timing_enable(1))
+    try:
+        for r in range(reps + 3):
+            color, _, _ = rasterize_batch(cat["means3D"], cat["opacities"], cat["scales"], cat["rotations"], vm, pm, cp,
+                                          bg, **kw)
+            color.backward(w)
+            _lib.check(_lib.lib.up3d_raster_timing_read(buf))
+            if r >= 3:
+                ms[r - 3] = list(buf)
+    finally:
+        _lib.check(_lib.lib.up3d_raster_timing_enable(0))
+    tot = float(ms.mean(0).sum())
+    I = P * (RES * RES // 256)
+    ref_bytes = B * V * (P * (240 + 36 * 4) + 108 * I + 40 * RES * RES)
+    return {"workload": f"{B} objects x {V} views, P=8192 Gaussians/object (reference scale regime), 256x256, fwd+bwd",
+            "ms": tot, "views_per_s": B * V / (tot * 1e-3),
+            "kernels_ms": {n: float(v) for n, v in zip(["project", "depth_sort", "blend_forward", "grad_clear",
+                                                         "blend_backward", "geometry_backward"], ms.mean(0))},
+            "reference_algorithm_bytes": ref_bytes,
+            "effective_GBs_vs_reference_traffic": ref_bytes / (tot * 1e-3) / 1e9,
+            "frac_of_hbm_peak_vs_reference_traffic": ref_bytes / (tot * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
+
+def ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    n_gpus = world
+    from unipre3d_b200 import _lib, synthetic
+    from unipre3d_b200.trainer import Trainer, _to_device
+    cfg = make_cfg(n_gpus)
+    use_graph = (world == 1) and not args.no_graph
+    autocast = None if args.fp32 else torch.bfloat16
+    trainer = Trainer(cfg, device=device, use_cuda_graph=use_graph, autocast_dtype=autocast)
+    n_batches = 4
+    batches = [synthetic.make_batch(cfg, OBJECTS_PER_GPU, N_POINTS, seed=1000 * rank + i, pin=True) for i in range(n_batches)]
+    h2d = synthetic.batch_nbytes(batches[0])
+    views_per_step = OBJECTS_PER_GPU * int(cfg.opt.imgs_per_obj) * n_gpus
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)     # > 126 MB L2
+    peaks, peak_kind = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also captures the CUDA graph)
+    for i in range(max(args.warmup, 3)):
+        trainer.train_iteration(batches[i % n_batches])
+    barrier()
+    launches_before = _lib.launch_count
+
+    def timed(step_fn):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for i in range(args.steps):
+            flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+            ev[i][0].record()
+            step_fn(i)
+            ev[i][1].record()
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident steps ("value"): inputs already in HBM
+    resident = _to_device(batches[0], device, non_blocking=False)
+    if use_graph:
+        trainer._copy_into_static(resident)
+        torch.cuda.synchronize()
+
+        def step_resident(i):
+            trainer._graph.replay()
+    else:
+        def step_resident(i):
+            trainer._step_body(resident)
+    with ClockSampler(local) as clk:
+        ms_resident = timed(step_resident)
+        # ---- end-to-end steps: pinned host batch -> H2D -> step -> D2H loss, through the public API
+        losses = []
+        ms_e2e = timed(lambda i: losses.append(trainer.train_iteration(batches[i % n_batches], read_loss=True)))
+    clocks = clk.summary()
+    # kernels of libunipre3d_b200 per step (FPS, subsample_group, project, depth_sort, blend_forward, focal_l2 x2,
+    # blend_backward, geometry_backward), counted from the C-ABI calls of one eager step; a graph replay launches
+    # the same kernel nodes
+    before = _lib.launch_count
+    trainer._step_body(resident)
+    torch.cuda.synchronize()
+    per_step_launches = _lib.launch_count - before
+    gpu_launches = per_step_launches * args.steps * 2
+
+    line = None
+    if rank == 0:
+        extra = {}
+        try:
+            # eager (no graph) pass with event hooks for the per-kernel numbers
+            extra.update(raster_roofline(trainer, resident, cfg, max(3, min(args.steps, 10)), peaks, peak_kind))
+            extra["raster_only"] = raster_only_headline(device, 5, peaks)
+        except Exception as e:  # never lose the headline because a side measurement failed
+            extra["roofline_error"] = repr(e)
+        cpu_baseline = None
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            try:
+                cb = run_cpu_port(args, as_reference=False)
+                cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:
+                cpu_baseline = {"error": repr(e)}
+        value = views_per_step / (ms_resident / args.steps * 1e-3)
+        e2e = views_per_step / (ms_e2e / args.steps * 1e-3)
+        line = {"metric": "views/sec (8192 pts->256^2 render), full pre-training step", "value": value,
+                "unit": "views/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None,
+                "dtype": "f32 rasterizer/point ops/loss/optimizer; backbone GEMMs " + ("f32" if args.fp32 else "bf16 (fp32 accumulate, fp32 master weights)"),
+                "data": "synthetic",
+                "config": {"workload": "transformer_pretraining: 8 objects x 4 rendered views per GPU, 8192-pt clouds, "
+                                       "256x256, 128 Gaussians/object, SH degree 1 (BASELINE.json configs[1])",
+                           "objects_per_gpu": OBJECTS_PER_GPU, "views_per_step": views_per_step, "parallelism": f"dp{n_gpus}",
+                           "cuda_graph": bool(use_graph),
+                           "l2": "256 MiB buffer written between timed iterations (L2 flush), per-step CUDA-event pairs"},
+                "clocks": clocks,
+                "e2e": {"value": e2e, "unit": "views/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": h2d * n_gpus, "d2h_bytes_per_step": 4 * n_gpus,
+                        "last_loss": losses[-1] if losses else None},
+                "gpu_launches": gpu_launches, "cpu_baseline": cpu_baseline}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fp32", action="store_true", help="keep the backbone GEMMs in fp32 (reference precision)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,9 +45,12 @@ def test_batched_step_equals_reference_shaped_loop():
                                  cfg.opt.bg_color_loss_rate)
     loss_b.backward()
     assert abs(float(loss_a) - float(loss_b)) <= 1e-6 * max(1.0, abs(float(loss_b)))
+    # conv biases feeding a BatchNorm have a mathematically zero gradient (pure rounding noise), hence the
+    # global-scale floor in the denominator
+    gmax = max(float(p.grad.abs().max()) for p in tr.params)
     worst = 0.0
     for ga, p in zip(grads_a, tr.params):
-        scale = float(p.grad.abs().max()) + 1e-8
+        scale = float(p.grad.abs().max()) + 1e-3 * gmax
         worst = max(worst, float((ga - p.grad).abs().max()) / scale)
     assert worst <= 2e-3, f"gradients of the batched step deviate from the per-view loop: rel {worst}"
 

@@ -22,7 +22,7 @@ class FeatureFusion:
         """feat_fusion.py:23-56.  c2w_matrix is the row-vector (transposed) camera-to-world 4x4."""
         ones = torch.ones([*center.shape[:2], 1], device=center.device, dtype=center.dtype)
         coords_h = torch.cat([center, ones], dim=2)
-        w2c = torch.linalg.inv(c2w_matrix.permute(0, 2, 1))
+        w2c = torch.linalg.inv_ex(c2w_matrix.permute(0, 2, 1)).inverse  # inv() without its blocking info check
         cam = torch.matmul(w2c, coords_h.transpose(1, 2)).transpose(1, 2)
         px = (cam[..., 0] * float(intrinsic[0][0])) / cam[..., 2] + float(intrinsic[0][2])
         py = (cam[..., 1] * float(intrinsic[1][1])) / cam[..., 2] + float(intrinsic[1][2])
