@@ -90,3 +90,26 @@ def test_cuda_graph_step_matches_eager_and_learns():
     assert np.isfinite(losses[True]).all() and np.isfinite(losses[False]).all()
     assert losses[False][-1] < losses[False][0], "eager loss does not decrease"
     assert abs(losses[True][0] - losses[False][3]) <= 5e-3 * abs(losses[False][3]) + 1e-5
+
+
+def test_lazy_image_features_equal_dense_dataflow():
+    """Sampling Conv1x1(GroupNorm(features)) at the projected pixels == indexing the dense tensor
+    (the reference's dataflow, gaussian_predictor.py:139 + feat_fusion.py:121-131): values and parameter gradients."""
+    from unipre3d_b200.fusion import LazyImageFeatures
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False          # the dense path is a cuDNN conv: compare in true fp32
+    n, Cin, Cout, R, N = 3, 128, 384, 32, 50
+    conv = torch.nn.Sequential(torch.nn.GroupNorm(32, Cin, eps=1e-6), torch.nn.Conv2d(Cin, Cout, 1)).cuda()
+    with torch.no_grad():
+        conv[0].weight.uniform_(0.5, 1.5); conv[0].bias.normal_()
+    x = torch.randn(n, Cin, R, R, device="cuda")
+    bidx = torch.arange(n, device="cuda").unsqueeze(1).expand(n, N)
+    ix, iy = torch.randint(0, R, (n, N), device="cuda"), torch.randint(0, R, (n, N), device="cuda")
+    w = torch.randn(n, N, Cout, device="cuda")
+    a = LazyImageFeatures(x, conv).sample(bidx, ix, iy)
+    ga = torch.autograd.grad((a * w).sum(), list(conv.parameters()))
+    b = conv(x)[bidx, :, ix, iy]
+    gb = torch.autograd.grad((b * w).sum(), list(conv.parameters()))
+    assert torch.allclose(a, b, atol=2e-5, rtol=1e-5)
+    for u, v in zip(ga, gb):
+        assert torch.allclose(u, v, atol=1e-4 * float(v.abs().max()) + 1e-6, rtol=1e-4)

@@ -127,16 +127,28 @@ class Encoder(nn.Module):
         self.second_conv = nn.Sequential(nn.Conv1d(512, 512, 1), nn.BatchNorm1d(512), nn.ReLU(inplace=True),
                                          nn.Conv1d(512, self.encoder_channel, 1))
 
+    @staticmethod
+    def _pointwise(conv: nn.Conv1d, x2d: torch.Tensor) -> torch.Tensor:
+        """Conv1d(kernel 1) on channels-last rows == one GEMM (rows x C_in) @ W^T; parameters keep Conv1d's shape."""
+        return F.linear(x2d, conv.weight.squeeze(-1), conv.bias)
+
     def forward(self, point_groups):
-        """point_groups: (B, G, K, 3) -> (B, G, C)"""
+        """point_groups: (B, G, K, 3) -> (B, G, C).  Same arithmetic as transformer.py:227-243, laid out
+        channels-last so the four 1x1 convolutions are plain GEMMs over B*G*K rows (BatchNorm1d on (rows, C) uses
+        the same per-channel statistics over all B*G*K samples as on (B*G, C, K))."""
         bs, g, n, _ = point_groups.shape
-        point_groups = point_groups.reshape(bs * g, n, 3)
-        feature = self.first_conv(point_groups.transpose(2, 1))
-        feature_global = torch.max(feature, dim=2, keepdim=True)[0]
-        feature = torch.cat([feature_global.expand(-1, -1, n), feature], dim=1)
-        feature = self.second_conv(feature)
-        feature_global = torch.max(feature, dim=2, keepdim=False)[0]
-        return feature_global.reshape(bs, g, self.encoder_channel)
+        rows = point_groups.reshape(bs * g * n, 3)
+        f = self._pointwise(self.first_conv[0], rows)
+        f = self.first_conv[2](self.first_conv[1](f))
+        f = self._pointwise(self.first_conv[3], f)                                   # (BGK, 256)
+        f3 = f.reshape(bs * g, n, -1)
+        fg = torch.max(f3, dim=1, keepdim=True)[0]                                   # (BG, 1, 256)
+        f = torch.cat([fg.expand(-1, n, -1), f3], dim=2).reshape(bs * g * n, -1)     # (BGK, 512) global || local
+        f = self._pointwise(self.second_conv[0], f)
+        f = self.second_conv[2](self.second_conv[1](f))
+        f = self._pointwise(self.second_conv[3], f)                                  # (BGK, C)
+        fg = torch.max(f.reshape(bs * g, n, -1), dim=1)[0]
+        return fg.reshape(bs, g, self.encoder_channel)
 
 
 class SubsampleGroup(nn.Module):
@@ -181,7 +193,7 @@ class PointTransformerEncoder(nn.Module):
             pts = pts["pos"]
         pts = pts[:, :, :3].contiguous()
         neighborhood, center = self.group_divider(pts)                       # (B,3,G,K), (B,G,3)
-        group_input_tokens = self.encoder(neighborhood.permute(0, 2, 3, 1))  # (B,G,C)
+        group_input_tokens = self.encoder(neighborhood.permute(0, 2, 3, 1))  # (B,G,K,3) -> (B,G,C)
         group_input_tokens = self.reduce_dim(group_input_tokens)
         cls_tokens = self.cls_token.expand(group_input_tokens.size(0), -1, -1)
         cls_pos = self.cls_pos.expand(group_input_tokens.size(0), -1, -1)

@@ -143,44 +143,56 @@ fps_streaming_kernel(int N, int M, int bs, int log2bs, const float *__restrict__
 //   here: 32 lanes test 32 consecutive points; ballot + popc keep the ascending-index order.
 // ------------------------------------------------------------------------------------------------
 constexpr int BQ_WARPS = 8;
+constexpr int BQ_TILE = 4096;   // points staged per shared-memory tile (48 KB: no opt-in, 4 CTAs / SM)
 
 template <bool FUSED>
 __global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(int N, int M, int K, float radius2, const float *__restrict__ new_xyz, const float *__restrict__ xyz,
                   const int32_t *__restrict__ fps_idx, int32_t *__restrict__ idx_out, float *__restrict__ center_out,
                   float *__restrict__ neigh_out) {
-    extern __shared__ int32_t s_idx[];  // [BQ_WARPS][K]
-    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ __align__(16) float s_pts[BQ_TILE * 3];   // AoS tile of the cloud; lane stride 3 words: conflict-free
+    extern __shared__ int32_t s_idx[];                   // [BQ_WARPS][K]
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = blockIdx.x * BQ_WARPS + warp;
-    if (m >= M) return;
+    const bool live = m < M;
     const float *pts = xyz + (size_t)b * N * 3;
-    float cx, cy, cz;
-    if (FUSED) {
-        const int ci = fps_idx[(size_t)b * M + m];
-        cx = pts[3 * ci]; cy = pts[3 * ci + 1]; cz = pts[3 * ci + 2];
-        if (lane < 3) center_out[((size_t)b * M + m) * 3 + lane] = lane == 0 ? cx : (lane == 1 ? cy : cz);
-    } else {
-        const float *c = new_xyz + ((size_t)b * M + m) * 3;
-        cx = c[0]; cy = c[1]; cz = c[2];
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (live) {
+        if (FUSED) {
+            const int ci = fps_idx[(size_t)b * M + m];
+            cx = pts[3 * ci]; cy = pts[3 * ci + 1]; cz = pts[3 * ci + 2];
+            if (lane < 3) center_out[((size_t)b * M + m) * 3 + lane] = lane == 0 ? cx : (lane == 1 ? cy : cz);
+        } else {
+            const float *c = new_xyz + ((size_t)b * M + m) * 3;
+            cx = c[0]; cy = c[1]; cz = c[2];
+        }
     }
     int32_t *my = s_idx + warp * K;
-    int cnt = 0, first = 0;
-    for (int k0 = 0; k0 < N && cnt < K; k0 += 32) {
-        const int k = k0 + lane;
-        bool hit = false;
-        if (k < N) {
-            const float dx = xsub(cx, pts[3 * k]), dy = xsub(cy, pts[3 * k + 1]), dz = xsub(cz, pts[3 * k + 2]);
-            const float d2 = xfma(dz, dz, xfma(dx, dx, xmul(dy, dy)));
-            hit = d2 < radius2;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (bal) {
-            if (cnt == 0) first = k0 + __ffs(bal) - 1;
-            const int slot = cnt + __popc(bal & lanemask_lt());
-            if (hit && slot < K) my[slot] = k;
-            cnt += __popc(bal);
+    int cnt = live ? 0 : K, first = 0;
+    for (int t0 = 0; t0 < N; t0 += BQ_TILE) {
+        const int tn = min(BQ_TILE, N - t0);
+        // every warp of the CTA already has its K neighbours -> stop streaming the cloud
+        if (__syncthreads_and(cnt >= K)) break;
+        for (int i = tid; i < tn * 3; i += BQ_WARPS * 32) s_pts[i] = pts[(size_t)t0 * 3 + i];
+        __syncthreads();
+        for (int k0 = 0; k0 < tn && cnt < K; k0 += 32) {
+            const int k = k0 + lane;
+            bool hit = false;
+            if (k < tn) {
+                const float dx = xsub(cx, s_pts[3 * k]), dy = xsub(cy, s_pts[3 * k + 1]), dz = xsub(cz, s_pts[3 * k + 2]);
+                const float d2 = xfma(dz, dz, xfma(dx, dx, xmul(dy, dy)));
+                hit = d2 < radius2;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {
+                if (cnt == 0) first = t0 + k0 + __ffs(bal) - 1;
+                const int slot = cnt + __popc(bal & lanemask_lt());
+                if (hit && slot < K) my[slot] = t0 + k;
+                cnt += __popc(bal);
+            }
         }
     }
+    if (!live) return;
     __syncwarp();
     cnt = min(cnt, K);
     for (int s = lane; s < K; s += 32) {

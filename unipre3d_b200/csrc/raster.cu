@@ -592,10 +592,30 @@ struct BlendBwdArgs {
     State st;
 };
 
+// Reduction strategy.  The gradient of Gaussian j sums, over the 256 pixels of the tile, nine terms that all factor
+// through two per-(pixel, entry) scalars  u = G * dL/dalpha  and  w = alpha * T :
+//     dL/dopac' = S0,   dL/drgb_c = sum w * dLdC_c,
+//     dL/dmean2D = -o (cx Sx + cy Sy, cz Sy + cy Sx),  dL/dconic = -o (Sxx/2, Sxy, Syy/2),
+// with S0 = sum u, Sx = sum u dx, Sy = sum u dy, Sxx = sum u dx^2, Sxy = sum u dx dy, Syy = sum u dy^2 and
+// (cx, cy, cz, o) the conic / opacity of the entry.  Phase 1 (one thread per pixel, sequential over a sub-batch of
+// BWD_EB entries, back to front) only produces u and w into shared memory; phase 2 (16 threads per entry) forms the
+// nine moment sums over the pixels with 4 shuffle levels, and one lane per entry issues the global atomics.  This
+// replaces 45 shuffles + 9 shared atomics per (warp, entry) of the straightforward scheme.
+constexpr int BWD_EB = 16;            // entries per sub-batch
+constexpr int BWD_ROW = 256 + 16;     // padded row of the u / w staging arrays (conflict-free phase-2 reads)
+
+struct BwdSmem {
+    TileChunk ch;
+    float u[BWD_EB][BWD_ROW];
+    float w[BWD_EB][BWD_ROW];
+    float dL[3][UP3D_TILE_PIX];
+    int red[8];
+};
+
 __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const BlendBwdArgs a) {
-    __shared__ TileChunk ch;
-    __shared__ float sacc[UP3D_TILE_PIX * 9];
-    __shared__ int s_red[8];
+    extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
+    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(bwd_smem_raw);
+    TileChunk &ch = sm.ch;
     const int v = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = tx * UP3D_TILE + (tid & 15), py = ty * UP3D_TILE + (tid >> 4);
@@ -607,15 +627,12 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
 
     const float T_final = inside ? a.st.final_T[v * HW + pix] : 0.f;
     const int last_contributor = inside ? a.st.n_contrib[v * HW + pix] : 0;
-    // tile-wide max of n_contrib
-    int m = last_contributor;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) s_red[warp] = m;
+    int m = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0) sm.red[warp] = m;
     __syncthreads();
     int Lmax = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) Lmax = max(Lmax, s_red[w]);
+    for (int w8 = 0; w8 < 8; ++w8) Lmax = max(Lmax, sm.red[w8]);
     if (Lmax == 0) return;
 
     float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
@@ -623,6 +640,7 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
         const float *g = a.dL_dcolor + (size_t)v * 3 * HW + pix;
         dLp0 = g[0]; dLp1 = g[HW]; dLp2 = g[2 * HW];
     }
+    sm.dL[0][tid] = dLp0; sm.dL[1][tid] = dLp1; sm.dL[2][tid] = dLp2;
     const float bg_dot = a.bg[0] * dLp0 + a.bg[1] * dLp1 + a.bg[2] * dLp2;
 
     // pass 1: how many 256-record chunks hold the first Lmax list entries of this tile
@@ -640,73 +658,93 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;     // accum_rec
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;        // last_color
     float last_alpha = 0.f;
+    // phase-2 role of this thread: entry slot e2 of the sub-batch, 16 pixels {part + 16 i}
+    const int e2 = tid >> 4, part = tid & 15;
 
     for (int c = c_last; c >= 0; --c) {
-        for (int j = tid; j < UP3D_TILE_PIX * 9; j += UP3D_TILE_PIX) sacc[j] = 0.f;
         const int cnt = load_compact_chunk<true>(ch, a.st, rec0, n, c * UP3D_TILE_PIX, tx, ty);  // syncs inside
         const int pos_base = running_end - cnt;  // 0-based list position of entry 0 of this chunk
         running_end = pos_base;
-        for (int j = cnt - 1; j >= 0; --j) {
-            const int pos = pos_base + j;
-            if (pos >= Lmax) continue;  // block-uniform
-            float g_mx = 0.f, g_my = 0.f, g_cx = 0.f, g_cy = 0.f, g_cz = 0.f, g_op = 0.f, g_r = 0.f, g_g = 0.f, g_b = 0.f;
-            bool active = pos < last_contributor;
-            if (active) {
-                const float2 xy = ch.xy[j];
-                const float4 co = ch.co[j];
-                const float dx = xy.x - pfx, dy = xy.y - pfy;
-                const float power = gauss_power(co, dx, dy);
-                active = !(power > 0.0f);
-                if (active) {
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, co.w * G);
-                    active = !(alpha < 1.0f / 255.0f);
-                    if (active) {
-                        T = T / (1.f - alpha);
-                        const float dchannel_dcolor = alpha * T;
-                        const float4 col = ch.rgb[j];
-                        acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                        acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                        acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                        lc0 = col.x; lc1 = col.y; lc2 = col.z;
-                        float dL_dalpha = (col.x - acc0) * dLp0 + (col.y - acc1) * dLp1 + (col.z - acc2) * dLp2;
-                        g_r = dchannel_dcolor * dLp0; g_g = dchannel_dcolor * dLp1; g_b = dchannel_dcolor * dLp2;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                        const float dL_dG = co.w * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * co.x - gdy * co.y;
-                        const float dG_ddely = -gdy * co.z - gdx * co.y;
-                        g_mx = dL_dG * dG_ddelx;
-                        g_my = dL_dG * dG_ddely;
-                        g_cx = -0.5f * gdx * dx * dL_dG;
-                        g_cy = -gdx * dy * dL_dG;
-                        g_cz = -0.5f * gdy * dy * dL_dG;
-                        g_op = G * dL_dalpha;
+        int jtop = min(cnt - 1, Lmax - 1 - pos_base);   // entries beyond the tile's max n_contrib never contribute
+        for (; jtop >= 0; jtop -= BWD_EB) {
+            // ---- phase 1: per pixel, entries jtop, jtop-1, ... (back to front)
+#pragma unroll 4
+            for (int e = 0; e < BWD_EB; ++e) {
+                const int j = jtop - e;
+                float u = 0.f, wgt = 0.f;
+                if (j >= 0 && pos_base + j < last_contributor) {
+                    const float2 xy = ch.xy[j];
+                    const float4 co = ch.co[j];
+                    const float dx = xy.x - pfx, dy = xy.y - pfy;
+                    const float power = gauss_power(co, dx, dy);
+                    if (!(power > 0.0f)) {
+                        const float G = expf(power);
+                        const float alpha = fminf(0.99f, co.w * G);
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            T = T / (1.f - alpha);
+                            wgt = alpha * T;
+                            const float4 col = ch.rgb[j];
+                            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                            lc0 = col.x; lc1 = col.y; lc2 = col.z;
+                            float dL_dalpha = (col.x - acc0) * dLp0 + (col.y - acc1) * dLp1 + (col.z - acc2) * dLp2;
+                            dL_dalpha *= T;
+                            last_alpha = alpha;
+                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                            u = G * dL_dalpha;
+                        }
                     }
                 }
+                sm.u[e][tid] = u;
+                sm.w[e][tid] = wgt;
             }
-            if (__any_sync(0xffffffffu, active)) {
-                g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_cx = warp_sum(g_cx); g_cy = warp_sum(g_cy);
-                g_cz = warp_sum(g_cz); g_op = warp_sum(g_op); g_r = warp_sum(g_r); g_g = warp_sum(g_g); g_b = warp_sum(g_b);
-                if (lane == 0) {
-                    float *s = sacc + j * 9;
-                    atomicAdd(s + 0, g_mx); atomicAdd(s + 1, g_my); atomicAdd(s + 2, g_cx); atomicAdd(s + 3, g_cy);
-                    atomicAdd(s + 4, g_cz); atomicAdd(s + 5, g_op); atomicAdd(s + 6, g_r); atomicAdd(s + 7, g_g);
-                    atomicAdd(s + 8, g_b);
+            __syncthreads();
+            // ---- phase 2: 16 threads per entry reduce the nine moment sums over the 256 pixels
+            {
+                const int j = jtop - e2;
+                float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, R0 = 0.f, R1 = 0.f, R2 = 0.f;
+                if (j >= 0) {
+                    const float2 xy = ch.xy[j];
+                    const float bx = xy.x - (float)(tx * UP3D_TILE + part), by0 = xy.y - (float)(ty * UP3D_TILE);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int p = part + 16 * i;         // pixel (column = part, row = i)
+                        const float u = sm.u[e2][p], wv = sm.w[e2][p];
+                        const float dx = bx, dy = by0 - (float)i;
+                        const float ux = u * dx, uy = u * dy;
+                        S0 += u; Sx += ux; Sy += uy;
+                        Sxx = fmaf(ux, dx, Sxx); Sxy = fmaf(ux, dy, Sxy); Syy = fmaf(uy, dy, Syy);
+                        R0 = fmaf(wv, sm.dL[0][p], R0); R1 = fmaf(wv, sm.dL[1][p], R1); R2 = fmaf(wv, sm.dL[2][p], R2);
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    S0 += __shfl_xor_sync(0xffffffffu, S0, o); Sx += __shfl_xor_sync(0xffffffffu, Sx, o);
+                    Sy += __shfl_xor_sync(0xffffffffu, Sy, o); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, o);
+                    Sxy += __shfl_xor_sync(0xffffffffu, Sxy, o); Syy += __shfl_xor_sync(0xffffffffu, Syy, o);
+                    R0 += __shfl_xor_sync(0xffffffffu, R0, o); R1 += __shfl_xor_sync(0xffffffffu, R1, o);
+                    R2 += __shfl_xor_sync(0xffffffffu, R2, o);
+                }
+                if (part == 0 && j >= 0) {
+                    const float4 co = ch.co[j];
+                    float *g = a.gacc + (size_t)(rec0 + ch.id[j]) * GACC_STRIDE;
+                    const float o_ = -co.w;
+                    const float v0 = o_ * (co.x * Sx + co.y * Sy), v1 = o_ * (co.z * Sy + co.y * Sx);
+                    const float v2 = 0.5f * o_ * Sxx, v3 = o_ * Sxy, v4 = 0.5f * o_ * Syy;
+                    if (v0 != 0.f) atomicAdd(g + 0, v0);
+                    if (v1 != 0.f) atomicAdd(g + 1, v1);
+                    if (v2 != 0.f) atomicAdd(g + 2, v2);
+                    if (v3 != 0.f) atomicAdd(g + 3, v3);
+                    if (v4 != 0.f) atomicAdd(g + 4, v4);
+                    if (S0 != 0.f) atomicAdd(g + 5, S0);
+                    if (R0 != 0.f) atomicAdd(g + 6, R0);
+                    if (R1 != 0.f) atomicAdd(g + 7, R1);
+                    if (R2 != 0.f) atomicAdd(g + 8, R2);
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid < cnt && pos_base + tid < Lmax) {
-            float *g = a.gacc + (size_t)(rec0 + ch.id[tid]) * GACC_STRIDE;
-            const float *s = sacc + tid * 9;
-#pragma unroll
-            for (int q = 0; q < 9; ++q)
-                if (s[q] != 0.f) atomicAdd(g + q, s[q]);
-        }
-        __syncthreads();
     }
 }
 
@@ -986,7 +1024,7 @@ struct Timing {
     cudaEvent_t ev[8];
     bool fwd_valid = false, bwd_valid = false;
 };
-static thread_local Timing g_timing;
+static Timing g_timing;  // process-wide: autograd runs the backward on its own host thread
 static inline void tick(int i, cudaStream_t s) {
     if (g_timing.enabled) cudaEventRecord(g_timing.ev[i], s);
 }
@@ -1089,7 +1127,8 @@ int up3d_raster_backward(const up3d_raster_desc *d, const float *means3D, const 
     tick(5, stream);
     if (V > 0) {
         BlendBwdArgs ba{d->width, d->height, d->view_rec_start, bg, dL_dcolor, sc.gacc, st};
-        blend_backward_kernel<<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, 0, stream>>>(ba);
+        UP3D_CUDA_OK(cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+        blend_backward_kernel<<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, sizeof(BwdSmem), stream>>>(ba);
         UP3D_LAUNCH_OK("blend_backward_kernel");
     }
     tick(6, stream);

@@ -27,6 +27,7 @@ import torch
 import torch.nn as nn
 
 from .backbone import PointTransformerEncoder
+from .fusion import LazyImageFeatures
 
 
 def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
@@ -152,7 +153,10 @@ class GaussianSplatPredictor(nn.Module):
         B, N_views = image.shape[0], image.shape[1]
         image = image.reshape(B * N_views, *image.shape[2:])
         image_output = self.image_network.forward(image)
-        image_features = self.image_conv.forward(image_output["decoder_block_3"])
+        if getattr(self.cfg.model, "dense_image_features", False):
+            image_features = self.image_conv.forward(image_output["decoder_block_3"])     # reference dataflow
+        else:
+            image_features = LazyImageFeatures(image_output["decoder_block_3"], self.image_conv)
         point_features, center = self.point_network.forward_feat_fusion(
             point_cloud, image_features, source_cameras_view_to_world, self.fusion_mlps, self.intrinsic)
         out = self._process_network_output(point_features.split(self.split_dimensions, dim=1), center)

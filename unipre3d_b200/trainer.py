@@ -179,6 +179,9 @@ class Trainer:
         self._static: Optional[dict] = None
         self._loss_buf = torch.zeros((), dtype=torch.float32, device=self.device)
         self._loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        # input pipelining: the next batch is copied host->device on a side stream while the current step runs
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._staged = None          # (key, device dict, ready event)
 
     # ---------------------------------------------------------------------------------------------
     def render_validation_views(self, gaussian_splats, data) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -235,13 +238,41 @@ class Trainer:
                 dst.copy_(src, non_blocking=True)
         cp(self._static, data)
 
-    def train_iteration(self, data, read_loss: bool = True):
+    def _stage(self, data) -> None:
+        """Start the H2D copy of `data` (pinned host dict) on the copy stream."""
+        if self._staged is not None and self._staged[0] is data:
+            return
+        self._copy_stream.wait_stream(torch.cuda.current_stream())   # staging buffers may still be read
+        with torch.cuda.stream(self._copy_stream):
+            dev = _to_device(data, self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (data, dev, ev)
+
+    def _take_staged(self, data):
+        """Device copy of `data`: the prefetched one when it matches, else a fresh (stream-ordered) H2D copy."""
+        if self._staged is not None and self._staged[0] is data:
+            _, dev, ev = self._staged
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for t in (list(dev["point_cloud"].values()) if isinstance(dev.get("point_cloud"), dict) else []) + \
+                    [v for v in dev.values() if torch.is_tensor(v)]:
+                t.record_stream(cur)     # allocated on the copy stream, consumed on the compute stream
+            self._staged = None
+            return dev
+        return _to_device(data, self.device)
+
+    def train_iteration(self, data, read_loss: bool = True, prefetch=None):
         """One optimisation step on a host (ideally pinned) batch dict.  Returns the loss (float) when
-        `read_loss` (a D2H read, as the reference's logging does) else the device scalar."""
+        `read_loss` (a D2H read, as the reference's logging does) else the device scalar.  `prefetch`: the NEXT
+        step's host batch; its H2D copy is overlapped with this step's compute."""
         self.iteration += 1
         mm = self.model_manager
         if not self.use_cuda_graph:
-            loss = self._step_body(_to_device(data, self.device))
+            dev = self._take_staged(data)
+            if prefetch is not None:
+                self._stage(prefetch)
+            loss = self._step_body(dev)
         else:
             if self._static is None:
                 self._static = _to_device(data, self.device, non_blocking=False)
@@ -256,7 +287,9 @@ class Trainer:
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     self._loss_buf.copy_(self._step_body(self._static))
-            self._copy_into_static(data)
+            self._copy_into_static(self._take_staged(data))     # D2D when prefetched, H2D otherwise
+            if prefetch is not None:
+                self._stage(prefetch)
             self._graph.replay()
             loss = self._loss_buf
         mm.scheduler_step()
