@@ -310,8 +310,10 @@ def ours(args):
         losses = []
         # (the next step's pinned batch is prefetched on a copy stream while this step computes; every step still
         #  moves its full input batch host->device inside the timed region and reads its loss back)
+        #  the loss of every step is read back device->host, consumed with a one-step lag as a logging loop would)
         ms_e2e = timed(lambda i: losses.append(trainer.train_iteration(
-            batches[i % n_batches], read_loss=True, prefetch=batches[(i + 1) % n_batches])))
+            batches[i % n_batches], read_loss="lagged", prefetch=batches[(i + 1) % n_batches])))
+        losses = [x for x in losses if x is not None] + [trainer.last_loss()]
     clocks = clk.summary()
     # kernels of libunipre3d_b200 per step (FPS, subsample_group, project, depth_sort, blend_forward, focal_l2 x2,
     # blend_backward, geometry_backward), counted from the C-ABI calls of one eager step; a graph replay launches

@@ -236,3 +236,13 @@ def gather(points, idx):
     out = np.zeros((B, Cc, M), np.float32)
     lib().up3d_oracle_gather(B, Cc, N, M, _p(points), _p(idx), _p(out))
     return out
+
+
+def eval_sh(deg: int, sh, pos, campos):
+    """A.5 colour (after +0.5 and clamp) for points `pos` seen from `campos`; sh (n,M,3). -> (rgb (n,3), clamped (n,3))"""
+    sh, pos, campos = _f32(sh), _f32(pos), _f32(campos)
+    n, M = sh.shape[0], sh.shape[1]
+    rgb = np.zeros((n, 3), np.float32)
+    cl = np.zeros((n, 3), np.uint8)
+    lib().up3d_oracle_eval_sh(int(deg), int(M), int(n), _p(sh), _p(pos), _p(campos), _p(rgb), _p(cl))
+    return rgb, cl

@@ -190,6 +190,12 @@ static void sh_to_rgb(int deg, int M, const float *sh /* M*3 */, const float *p,
     }
 }
 
+/* exported for the golden-vector test against the reference's in-tree SH restatement (utils/sh_utils.py:57-112) */
+void up3d_oracle_eval_sh(int deg, int M, int n, const float *sh /* n*M*3 */, const float *pos /* n*3 */,
+                         const float *campos /* 3 */, float *rgb /* n*3 */, uint8_t *clamped /* n*3 */) {
+    for (int i = 0; i < n; ++i) sh_to_rgb(deg, M, sh + (size_t)i * M * 3, pos + 3 * i, campos, rgb + 3 * i, clamped + 3 * i);
+}
+
 static inline float ndc2pix(float v, int S) {
     /* ((v + 1.0) * S - 1.0) * 0.5 in double (A.1 step 7); nvcc contracts (..)*S - 1.0 into one fma */
     return (float)(fma((double)v + 1.0, (double)S, -1.0) * 0.5);

@@ -1,0 +1,112 @@
+"""Host-side logic that needs no GPU: config surface, layouts, synthetic batches, EMA schedule, sharding,
+state-dict naming, and the CPU port of the step."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_config_surface_and_overrides():
+    from unipre3d_b200.config import compose
+    cfg = compose()
+    assert cfg.model.backbone_type == "transformer" and cfg.model.max_sh_degree == 1 and cfg.model.isotropic is False
+    assert cfg.data.fov == pytest.approx(49.13434264120263) and cfg.data.training_resolution == 128
+    assert cfg.data.znear == 0.5 and cfg.data.zfar == 2 and cfg.data.white_background is False
+    assert cfg.opt.batch_size == 32 and cfg.opt.imgs_per_obj == 4 and cfg.opt.loss == "focal_l2"
+    assert cfg.opt.ema.beta == 0.9999 and cfg.opt.betas == [0.9, 0.999] and cfg.general.multiple_gpu is False
+    assert hasattr(cfg.data, "training_resolution") and not hasattr(cfg.data, "training_height")
+    c2 = compose(overrides=["opt.batch_size=8", "general.device=[0,1]", "data.training_resolution=256"])
+    assert c2.opt.batch_size == 8 and c2.general.multiple_gpu is True and c2.data.training_resolution == 256
+    with pytest.raises(FileNotFoundError):
+        compose("does_not_exist")
+
+
+def test_raster_layout_indexing():
+    from unipre3d_b200.rasterizer import RasterLayout
+    lay = RasterLayout([5, 0, 7], [2, 1, 3], torch.device("cpu"))
+    assert lay.n_sets == 3 and lay.n_views == 6 and lay.n_gaussians == 12 and lay.max_set_size == 7
+    assert lay.set_offsets.tolist() == [0, 5, 5, 12]
+    assert lay.set_view_start.tolist() == [0, 2, 3, 6]
+    assert lay.view_set.tolist() == [0, 0, 1, 2, 2, 2]
+    assert lay.view_rec_start.tolist() == [0, 5, 10, 10, 17, 24, 31] and lay.n_records == 31
+    assert RasterLayout.get([4], [1], "cpu") is RasterLayout.get([4], [1], "cpu")
+
+
+def test_synthetic_batch_matches_loader_contract():
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.config import compose
+    cfg = compose(overrides=["data.training_resolution=32"])
+    b = synthetic.make_batch(cfg, 3, 256, seed=0)
+    V = 5
+    assert b["gt_images"].shape == (3, V, 3, 32, 32) and b["point_cloud"]["pos"].shape == (3, 256, 3)
+    for k in ("world_view_transforms", "view_to_world_transforms", "full_proj_transforms"):
+        assert b[k].shape == (3, V, 4, 4)
+    pos = b["point_cloud"]["pos"]
+    assert torch.allclose(pos.mean(1), torch.zeros(3, 3), atol=1e-2) and float(pos.norm(dim=-1).max()) <= 0.5 + 1e-6
+    wv, vw, cc = b["world_view_transforms"][0, 0], b["view_to_world_transforms"][0, 0], b["camera_centers"][0, 0]
+    assert torch.allclose(wv @ vw, torch.eye(4), atol=1e-5)                       # row-vector convention inverses
+    assert torch.allclose(cc, vw[3, :3], atol=1e-5) and abs(float(cc.norm()) - 1.75) < 1e-4
+    p = torch.tensor([0.0, 0.0, 0.0, 1.0]) @ b["full_proj_transforms"][0, 0]      # origin projects to image centre
+    assert abs(float(p[0] / p[3])) < 1e-5 and abs(float(p[1] / p[3])) < 1e-5
+    gt = b["gt_images"]
+    bgfrac = float((gt.sum(2) == 0).float().mean())
+    assert 0.2 < bgfrac < 0.95
+
+
+def test_ema_schedule_and_shard_batch():
+    from unipre3d_b200.trainer import EMA, shard_batch
+    lin = torch.nn.Linear(2, 2)
+    ema = EMA(lin, beta=0.9999, update_every=10, update_after_step=100)
+    w0 = lin.weight.detach().clone()
+    ema.update()
+    assert torch.equal(ema.ema_model.weight, w0)
+    with torch.no_grad():
+        lin.weight.add_(1.0)
+    for _ in range(99):
+        ema.update()                       # steps 1..99: copies at multiples of 10 (still <= update_after_step)
+    assert torch.equal(ema.ema_model.weight, lin.weight)
+    ema.step = 200
+    assert ema.current_decay() == pytest.approx(1 - (1 + 99) ** (-2 / 3))
+    with torch.no_grad():
+        lin.weight.add_(1.0)
+    ema.update()
+    d = ema.current_decay.__func__(ema) if False else None
+    assert not torch.equal(ema.ema_model.weight, lin.weight)
+    data = {"a": torch.arange(8).view(8, 1), "point_cloud": {"pos": torch.arange(16).view(8, 2)}}
+    s = shard_batch(data, 1, 4)
+    assert s["a"].flatten().tolist() == [2, 3] and s["point_cloud"]["pos"].shape == (2, 2)
+    with pytest.raises(ValueError):
+        shard_batch(data, 0, 3)
+
+
+def test_state_dict_keys_follow_reference_naming():
+    from unipre3d_b200.config import compose
+    from unipre3d_b200.gaussian_predictor import GaussianSplatPredictor
+    m = GaussianSplatPredictor(compose())
+    keys = set(m.state_dict().keys())
+    for k in ["point_network.encoder.encoder.first_conv.0.weight", "point_network.encoder.encoder.second_conv.3.bias",
+              "point_network.encoder.reduce_dim.weight", "point_network.encoder.cls_token", "point_network.encoder.cls_pos",
+              "point_network.encoder.pos_embed.0.weight", "point_network.encoder.blocks.blocks.15.attn.qkv.weight",
+              "point_network.encoder.blocks.blocks.0.mlp.fc2.bias", "point_network.encoder.norm.weight",
+              "point_network.final.0.weight", "point_network.final.2.bias", "fusion_mlps.0.weight", "image_conv.0.weight",
+              "image_conv.1.bias", "sh_to_v_transform", "v_to_sh_transform"]:
+        assert k in keys, k
+    assert "point_network.encoder.blocks.blocks.0.attn.qkv.bias" not in keys        # qkv_bias=False
+    n_enc = sum(p.numel() for p in m.point_network.encoder.parameters())
+    assert n_enc == 29066880                                                        # SURVEY.md §2.2 (measured on the reference)
+
+
+def test_cpu_port_step_runs_and_learns():
+    from oracle.cpu_step import CpuStepper
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.config import compose
+    cfg = compose(overrides=["data.training_resolution=32", "opt.batch_size=2", "opt.imgs_per_obj=2"])
+    torch.manual_seed(0)
+    st = CpuStepper(cfg)
+    for m in st.model.modules():
+        if m.__class__.__name__ == "DropPath":
+            m.drop_prob = 0.0
+    d = synthetic.make_batch(cfg, 2, 512, seed=0)
+    losses = [st.step(d) for _ in range(4)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]

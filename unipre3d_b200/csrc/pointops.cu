@@ -143,7 +143,7 @@ fps_streaming_kernel(int N, int M, int bs, int log2bs, const float *__restrict__
 //   here: 32 lanes test 32 consecutive points; ballot + popc keep the ascending-index order.
 // ------------------------------------------------------------------------------------------------
 constexpr int BQ_WARPS = 8;
-constexpr int BQ_TILE = 4096;   // points staged per shared-memory tile (48 KB: no opt-in, 4 CTAs / SM)
+constexpr int BQ_TILE = 3072;   // points staged per shared-memory tile (36 KB static + K ints per warp dynamic < 48 KB)
 
 template <bool FUSED>
 __global__ void __launch_bounds__(BQ_WARPS * 32)

@@ -45,6 +45,19 @@ def prepare_model_inputs(data, cfg, bs_per_gpu, device):
     return _to_device(inputs, device)
 
 
+def shard_batch(data, rank: int, world: int):
+    """Objects are the unit of data parallelism: rank r owns objects [r*B/world, (r+1)*B/world) of a
+    global batch dict, with all of their views (the scene branch of the reference shards the same way through
+    DistributedSampler, train_network.py:55-71,95-103)."""
+    def cut(t):
+        B = t.shape[0]
+        if B % world != 0:
+            raise ValueError(f"global batch of {B} objects does not divide over {world} ranks")
+        per = B // world
+        return t[rank * per:(rank + 1) * per]
+    return {k: ({kk: cut(vv) for kk, vv in v.items()} if isinstance(v, dict) else cut(v)) for k, v in data.items()}
+
+
 class EMA:
     """Exponential moving average of the model weights with ema_pytorch's default schedule (the reference
     wraps the model in ema_pytorch.EMA(beta, update_every, update_after_step), train_network.py:188-198):
@@ -179,6 +192,8 @@ class Trainer:
         self._static: Optional[dict] = None
         self._loss_buf = torch.zeros((), dtype=torch.float32, device=self.device)
         self._loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._loss_ev = [None, None]
         # input pipelining: the next batch is copied host->device on a side stream while the current step runs
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._staged = None          # (key, device dict, ready event)
@@ -221,7 +236,7 @@ class Trainer:
         coef = torch.where(torch.isfinite(coef), coef, torch.zeros_like(coef))
         torch._foreach_mul_(grads, coef)
         mm.optimizer.step()
-        mm.optimizer.zero_grad(set_to_none=False)
+        mm.optimizer.zero_grad(set_to_none=True)   # grads are re-materialised at the same graph-pool addresses on replay
 
     def _step_body(self, data) -> torch.Tensor:
         loss = self._forward_backward(data)
@@ -295,8 +310,29 @@ class Trainer:
         mm.scheduler_step()
         if mm.ema:
             mm.ema.update()
+        if read_loss == "lagged":
+            # D2H read of THIS step's loss is enqueued now and consumed one step later (logging lags by one step),
+            # so the host never stalls the launch pipeline; returns the previous step's loss (None on the first call)
+            slot = self.iteration & 1
+            self._loss_ring[slot].copy_(loss, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._loss_ev[slot] = ev
+            prev = self._loss_ev[slot ^ 1]
+            if prev is None:
+                return None
+            prev.synchronize()
+            return float(self._loss_ring[slot ^ 1])
         if read_loss:
             self._loss_host.copy_(loss, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(self._loss_host)
         return loss
+
+    def last_loss(self) -> float:
+        """Blocks for the most recent step's lagged loss read."""
+        slot = self.iteration & 1
+        if self._loss_ev[slot] is None:
+            raise RuntimeError("no lagged loss read in flight")
+        self._loss_ev[slot].synchronize()
+        return float(self._loss_ring[slot])
