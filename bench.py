@@ -252,12 +252,13 @@ def ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     n_gpus = world
     from unipre3d_b200 import _lib, synthetic
     from unipre3d_b200.trainer import Trainer, _to_device
     cfg = make_cfg(n_gpus)
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     autocast = None if args.fp32 else torch.bfloat16
     trainer = Trainer(cfg, device=device, use_cuda_graph=use_graph, autocast_dtype=autocast)
     n_batches = 4
@@ -325,14 +326,18 @@ def ours(args):
     gpu_launches = per_step_launches * args.steps * 2
 
     line = None
+    extra = {}
+    try:
+        # eager (no graph) pass with event hooks for the per-kernel numbers; EVERY rank runs it (the model's
+        # SyncBatchNorm layers are collectives when N > 1), rank 0 reports
+        extra.update(raster_roofline(trainer, resident, cfg, max(3, min(args.steps, 10)), peaks, peak_kind))
+    except Exception as e:  # never lose the headline because a side measurement failed
+        extra["roofline_error"] = repr(e)
     if rank == 0:
-        extra = {}
         try:
-            # eager (no graph) pass with event hooks for the per-kernel numbers
-            extra.update(raster_roofline(trainer, resident, cfg, max(3, min(args.steps, 10)), peaks, peak_kind))
             extra["raster_only"] = raster_only_headline(device, 5, peaks)
-        except Exception as e:  # never lose the headline because a side measurement failed
-            extra["roofline_error"] = repr(e)
+        except Exception as e:
+            extra["raster_only_error"] = repr(e)
         cpu_baseline = None
         if n_gpus == 1 and not args.no_cpu_baseline:
             try:
@@ -362,7 +367,12 @@ def ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        # tearing the NCCL communicator down while CUDA graphs that captured its kernels are alive can hang:
+        # release the graph first, then skip the (optional) orderly teardown altogether
+        trainer._graph = None
+        os._exit(0)
 
 
 def main():

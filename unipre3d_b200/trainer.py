@@ -113,18 +113,24 @@ class ModelManager:
         self.optimizer = torch.optim.AdamW(groups, lr=0.0 if not capturable else torch.tensor(0.0, device=device),
                                            eps=1e-15, betas=tuple(cfg.opt.betas), fused=True, capturable=capturable)
         self.step_lr, self.lr_gamma, self._sched_step = cfg.opt.step_lr, cfg.opt.lr_gamma, 0
-        self.ddp = None
-        if cfg.general.multiple_gpu and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world > 1:
+            # train_network.py:183-186: SyncBatchNorm + data parallelism.  The gradient exchange is one NCCL
+            # all-reduce of a flat fp32 buffer per step (Trainer._allreduce_grads) instead of DDP's bucket hooks, so
+            # that the whole step -- collectives included -- can be captured into one CUDA graph.
             self.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.model)
-            self.ddp = torch.nn.parallel.DistributedDataParallel(
-                self.model, device_ids=[device.index], output_device=device.index, broadcast_buffers=False,
-                find_unused_parameters=False, gradient_as_bucket_view=True, bucket_cap_mb=64)
+            with torch.no_grad():
+                for t in list(self.model.parameters()) + list(self.model.buffers()):
+                    c = t if t.is_contiguous() else t.contiguous()
+                    dist.broadcast(c, src=0)
+                    if c is not t:
+                        t.copy_(c)
         self.ema = EMA(self.model, beta=cfg.opt.ema.beta, update_every=cfg.opt.ema.update_every,
                        update_after_step=cfg.opt.ema.update_after_step) if cfg.opt.ema.use else None
 
     @property
     def forward_model(self):
-        return self.ddp if self.ddp is not None else self.model
+        return self.model
 
     def scheduler_step(self):
         """StepLR(step_size=opt.step_lr, gamma=opt.lr_gamma) (train_network.py:160-163), in place."""
@@ -187,6 +193,8 @@ class Trainer:
         self.found_inf = torch.zeros((), dtype=torch.float32, device=self.device)
         self.model_manager.optimizer.grad_scale = None
         self.model_manager.optimizer.found_inf = self.found_inf
+        self._flat_grad = None
+        self._flat_views = None
         self.iteration = 0
         self._graph = None
         self._static: Optional[dict] = None
@@ -224,6 +232,27 @@ class Trainer:
         loss.backward()
         return loss.detach()
 
+    def _allreduce_grads(self) -> None:
+        """N > 1: average the gradients over ranks with ONE NCCL all-reduce of a flat fp32 buffer
+        (~118 MB for the transformer backbone), then point every p.grad at its slice."""
+        if self.world == 1:
+            return
+        grads = [p.grad for p in self.params]
+        if any(g is None for g in grads):
+            raise RuntimeError("a trainable parameter received no gradient (data-parallel ranks would diverge)")
+        if self._flat_grad is None:
+            n = sum(p.numel() for p in self.params)
+            self._flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self._flat_views, off = [], 0
+            for p in self.params:
+                self._flat_views.append(self._flat_grad[off: off + p.numel()].view_as(p))
+                off += p.numel()
+        torch._foreach_copy_(self._flat_views, grads)
+        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
+        self._flat_grad.mul_(1.0 / self.world)
+        for p, v in zip(self.params, self._flat_views):
+            p.grad = v
+
     def _clip_and_step(self) -> None:
         """368-390 + 343-344: total norm on the device; non-finite -> found_inf=1 -> fused AdamW leaves
         parameters and moments untouched; else grads are scaled to max_norm 1.0."""
@@ -240,6 +269,7 @@ class Trainer:
 
     def _step_body(self, data) -> torch.Tensor:
         loss = self._forward_backward(data)
+        self._allreduce_grads()
         self._clip_and_step()
         return loss
 
@@ -300,7 +330,7 @@ class Trainer:
                 torch.cuda.current_stream().wait_stream(s)
                 torch.cuda.synchronize()
                 self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph):
+                with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
                     self._loss_buf.copy_(self._step_body(self._static))
             self._copy_into_static(self._take_staged(data))     # D2D when prefetched, H2D otherwise
             if prefetch is not None:
