@@ -71,6 +71,14 @@ UP3D_API int up3d_gather_points(int B, int C, int N, int M, const float *points,
 UP3D_API int up3d_gather_points_grad(int B, int C, int N, int M, const float *grad_out, const int32_t *idx,
                             float *grad_points, up3d_stream_t stream);
 
+/* k nearest neighbours of each query among xyz (pointMLP's knn_point, openpoints/models/backbone/pointmlp.py:102-113,
+ * and -- with K = 3 and dist != NULL -- the 3-NN search of PointNetFeaturePropagation, pointmlp.py:397-403, which
+ * the reference does with a FULL sort of the (N x S) distance matrix).  xyz (B,N,D), query (B,S,D), D = 3 or 4
+ * (pointMLP with in_channels = 4 measures distances over xyz+height) -> idx (B,S,K) int32 in ascending distance,
+ * dist (B,S,K) squared distances |q|^2+|p|^2-2q.p or NULL.  K <= 64. */
+UP3D_API int up3d_knn(int B, int N, int S, int K, int D, const float *xyz, const float *query, int32_t *idx,
+                      float *dist, up3d_stream_t stream);
+
 /* Fused SubsampleGroup tail (openpoints/models/layers/group_embed.py:39-57 + group.py:235-255):
  * centres = xyz[fps_idx]; idx = ball_query(radius, K, xyz, centres);
  * neighborhood[b, :, g, k] = xyz[b, idx[b,g,k], :] - centres[b, g, :]   -> (B,3,G,K)

@@ -184,6 +184,60 @@ def main():
     np.savez_compressed(os.path.join(OUT, "utils.npz"), r=r.numpy(), gt=gt.numpy(), gt_w=gt_w.numpy(),
                         l_black=float(l_black), l_white=float(l_white), R=Rm, t=t, w2v=w2v, v2w=v2w, proj=pm,
                         sh=sh.numpy(), dirs=dirs.numpy(), **shv)
+    # ---------------------------------------------------------------- pointMLP encoder/decoder (small config, in_channels=4)
+    from oracle import oracle_lib as ol
+
+    def ref_fps(xyz, npoint):
+        """what the reference's CUDA kernel does with a (B,N,C) buffer: it indexes it as (B,N,3)
+        (sampling_gpu.cu:117-131) -- replayed by the CPU oracle on the same reinterpretation"""
+        B, N, C = xyz.shape
+        flat = xyz.detach().contiguous().reshape(-1).numpy()
+        view = np.lib.stride_tricks.as_strided(flat, (B, N, 3), (N * 3 * 4, 12, 4)).copy()
+        return torch.from_numpy(ol.fps(view, npoint))
+
+    layers = sys.modules["openpoints.models.layers"]
+    for n in ("random_sample", "LocalAggregation", "create_convblock2d", "three_interpolate", "three_nn",
+              "gather_operation", "create_linearblock", "create_convblock1d", "create_grouper", "fps"):
+        setattr(layers, n, None)
+    layers.furthest_point_sample = ref_fps
+    layers.__path__ = []
+    stub("openpoints.models.layers.group", QueryAndGroup=None)
+    pkg = stub("openpoints.models.backbone"); pkg.__path__ = []
+    sys.modules["openpoints.models"].__path__ = []
+    sys.modules["openpoints"].__path__ = []
+    pm_mod = load("openpoints.models.backbone.pointmlp", os.path.join(REF, "openpoints/models/backbone/pointmlp.py"))
+    torch.manual_seed(4)
+    B, N, R = 2, 64, 16
+    kw = dict(in_channels=4, embed_dim=8, groups=1, res_expansion=1.0, activation="relu", bias=False, use_xyz=False,
+              normalize="anchor", dim_expansion=[2, 2, 2, 2], pre_blocks=[2, 2, 2, 2], pos_blocks=[2, 2, 2, 2],
+              k_neighbors=[4, 4, 4, 4], reducers=[2, 2, 2, 2], de_blocks=[2, 2, 2, 2], de_dims=[64, 32, 16, 16])
+    enc = pm_mod.PointMLPEncoder(**kw)
+    with torch.no_grad():
+        for m in enc.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+        for g in enc.local_grouper_list:
+            g.affine_alpha.uniform_(0.5, 1.5); g.affine_beta.normal_(0, 0.2)
+    xyz = torch.randn(B, N, 3) * 0.25
+    p4 = torch.cat([xyz, xyz[:, :, 2:3] - xyz[:, :, 2:3].min(1, keepdim=True)[0]], -1)
+    img = torch.randn(B, 16, R, R, requires_grad=True)
+    fusion_mlps = torch.nn.Sequential(torch.nn.Linear(32, 16), torch.nn.ReLU())
+    c2w = torch.stack([cam.make_view(*cam.look_at_pose(40.0 * i, 25.0, 1.75), proj)["view_to_world_transform"] for i in range(B)]).unsqueeze(1)
+    K3 = np.zeros((3, 4)); focal = (R / 2.0) / math.tan(math.radians(fov / 2.0))
+    K3[0, 0] = K3[1, 1] = focal; K3[0, 2] = K3[1, 2] = R / 2.0; K3[2, 2] = 1
+    enc.train()
+    out, p_out = enc({"pos": p4}, img, c2w, fusion_mlps, K3)
+    wsum = torch.randn_like(out)
+    (out * wsum).sum().backward()
+    fps_stage1 = ref_fps(p4, N // 2)
+    enc.eval()
+    out_eval, _ = enc({"pos": p4}, img, c2w, fusion_mlps, K3)
+    np.savez_compressed(os.path.join(OUT, "pointmlp_encoder.npz"), p4=p4.numpy(), img=img.detach().numpy(), c2w=c2w.numpy(),
+                        intrinsic=K3, wsum=wsum.numpy(), out_train=out.detach().numpy(), out_eval=out_eval.detach().numpy(),
+                        p_out=p_out.numpy(), grad_img=img.grad.numpy(), fps_stage1=fps_stage1.numpy(),
+                        fusion_w=fusion_mlps[0].weight.detach().numpy(), fusion_b=fusion_mlps[0].bias.detach().numpy(),
+                        **{"sd." + k: v.detach().numpy() for k, v in enc.state_dict().items()},
+                        **{"grad." + k: q.grad.numpy() for k, q in enc.named_parameters() if q.grad is not None})
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 

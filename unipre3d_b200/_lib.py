@@ -41,6 +41,7 @@ def _load() -> C.CDLL:
         "up3d_gather_points": (i32, [i32, i32, i32, i32, vp, vp, vp, vp]),
         "up3d_gather_points_grad": (i32, [i32, i32, i32, i32, vp, vp, vp, vp]),
         "up3d_subsample_group": (i32, [i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+        "up3d_knn": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_raster_state_bytes": (C.c_size_t, [D]),
         "up3d_raster_scratch_bytes": (C.c_size_t, [D]),
         "up3d_raster_forward": (i32, [D] + [vp] * 16),
@@ -61,7 +62,7 @@ def _load() -> C.CDLL:
 lib = _load()
 EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_resident_points", "up3d_ball_query",
             "up3d_group_points", "up3d_group_points_grad", "up3d_gather_points", "up3d_gather_points_grad",
-            "up3d_subsample_group", "up3d_raster_state_bytes", "up3d_raster_scratch_bytes", "up3d_raster_forward",
+            "up3d_subsample_group", "up3d_knn", "up3d_raster_state_bytes", "up3d_raster_scratch_bytes", "up3d_raster_forward",
             "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_focal_l2_loss",
             "up3d_raster_timing_enable", "up3d_raster_timing_read"]
 

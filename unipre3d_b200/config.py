@@ -72,10 +72,13 @@ _TRANSFORMER = {
             "batch_size": 32, "test_generation_num": 1, "loss": "focal_l2", "non_bg_color_loss_rate": 4,
             "bg_color_loss_rate": 1, "step_lr": 20000, "lr_gamma": 0.8, "start_lpips_after": 50000},
 }
+_POINTMLP = copy.deepcopy(_TRANSFORMER)
+_POINTMLP["model"].update({"backbone_type": "pointmlp", "in_channels": 4})
 BUILTIN = {
     "settings": _SETTINGS,
     "dataset/shapenet": _SHAPENET,
     "transformer_pretraining": {"defaults": ["/settings@_here_", "/dataset/shapenet@_here_"], **_TRANSFORMER},
+    "pointmlp_pretraining": {"defaults": ["/settings@_here_", "/dataset/shapenet@_here_"], **_POINTMLP},
     "default_config": {"defaults": ["/transformer_pretraining@_here_"]},
 }
 

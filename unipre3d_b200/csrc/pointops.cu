@@ -208,6 +208,113 @@ ball_query_kernel(int N, int M, int K, float radius2, const float *__restrict__ 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k nearest neighbours (pointMLP LocalGrouper, /root/reference/openpoints/models/backbone/pointmlp.py:102-113,
+// 160-166) and 3-NN inverse-distance weights (PointNetFeaturePropagation, pointmlp.py:397-409).
+//   reference: materialises the (S x N) squared-distance matrix with a batched GEMM (128 MB per object at
+//   S=4096, N=8192) and runs torch.topk / a FULL torch.sort over it.
+//   here: one WARP per query streams the cloud from a shared-memory tile; each lane keeps the K/32 (rounded up)
+//   best candidates of its own strided subset... no: a warp-wide sorted list of the K best is kept distributed over
+//   the lanes (slot s lives in lane s%32, register s/32); a candidate better than the current worst is inserted with
+//   a ballot + shuffle shift.  The distance matrix is never written.
+// Distances are |q|^2 + |p|^2 - 2 q.p evaluated in fp32 like the reference's formula (square_distance); ties at the
+// K-th place may resolve differently from cuBLAS+topk (the reference's own order is unspecified: sorted=False).
+// ------------------------------------------------------------------------------------------------
+constexpr int KNN_WARPS = 8;
+constexpr int KNN_TILE = 2048;      // points per shared-memory tile (SoA x,y,z,|p|^2 : 32 KB)
+constexpr int KNN_MAXR = 2;         // K <= 64
+
+template <int R, int D>   // R = ceil(K / 32) registers per lane; D = point dimension (3, or 4: pointMLP's xyz+height)
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_kernel(int N, int S, int K, const float *__restrict__ xyz, const float *__restrict__ query,
+           int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+    __shared__ float sx[KNN_TILE], sy[KNN_TILE], sz[KNN_TILE], sw[D == 4 ? KNN_TILE : 1], sn[KNN_TILE];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x * KNN_WARPS + warp;
+    const bool live = q < S;
+    const float *pts = xyz + (size_t)b * N * D;
+    float qx = 0.f, qy = 0.f, qz = 0.f, qw = 0.f;
+    if (live) {
+        const float *qq = query + ((size_t)b * S + q) * D;
+        qx = qq[0]; qy = qq[1]; qz = qq[2];
+        if (D == 4) qw = qq[3];
+    }
+    const float qn = qx * qx + qy * qy + qz * qz + qw * qw;
+    // sorted ascending list of the K best: element s in lane s % 32, register s / 32
+    float bd[R];
+    int bi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { bd[r] = INFINITY; bi[r] = 0; }
+    float worst = INFINITY;   // distance of list element K-1 (warp-uniform)
+    for (int t0 = 0; t0 < N; t0 += KNN_TILE) {
+        const int tn = min(KNN_TILE, N - t0);
+        __syncthreads();
+        for (int i = tid; i < tn; i += KNN_WARPS * 32) {
+            const float *pp = pts + (size_t)(t0 + i) * D;
+            const float x = pp[0], y = pp[1], z = pp[2], w = D == 4 ? pp[3] : 0.f;
+            sx[i] = x; sy[i] = y; sz[i] = z; sn[i] = x * x + y * y + z * z + w * w;
+            if (D == 4) sw[i] = w;
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int k0 = 0; k0 < tn; k0 += 32) {
+            const int k = k0 + lane;
+            float d = INFINITY;
+            if (k < tn) {
+                float dot = qx * sx[k] + qy * sy[k] + qz * sz[k];
+                if (D == 4) dot += qw * sw[k];
+                d = (qn + sn[k]) - 2.f * dot;
+            }
+            unsigned cand = __ballot_sync(0xffffffffu, d < worst);
+            while (cand) {   // insert the candidates one by one (rare after the first few tiles)
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const float dn = __shfl_sync(0xffffffffu, d, src);
+                const int in = t0 + k0 + src;
+                if (!(dn < worst)) continue;      // the list may have tightened since the ballot
+                // position = number of list elements <= dn (stable: equal distances keep the earlier index first)
+                int pos = 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) pos += __popc(__ballot_sync(0xffffffffu, (r * 32 + lane) < K && bd[r] <= dn));
+                // shift elements [pos, K-2] up by one slot, highest register first
+#pragma unroll
+                for (int r = R - 1; r >= 0; --r) {
+                    const int s = r * 32 + lane;
+                    // slot s takes slot s-1: lane-1 of the same register, or lane 31 of the register below
+                    // (r is a compile-time constant after unrolling, so every shuffle is executed by the full warp)
+                    const float up_d = __shfl_up_sync(0xffffffffu, bd[r], 1);
+                    const int up_i = __shfl_up_sync(0xffffffffu, bi[r], 1);
+                    float lo_d = 0.f;
+                    int lo_i = 0;
+                    if (r > 0) {
+                        lo_d = __shfl_sync(0xffffffffu, bd[r > 0 ? r - 1 : 0], 31);
+                        lo_i = __shfl_sync(0xffffffffu, bi[r > 0 ? r - 1 : 0], 31);
+                    }
+                    const float pd = lane == 0 ? lo_d : up_d;
+                    const int pi = lane == 0 ? lo_i : up_i;
+                    if (s > pos && s < K) { bd[r] = pd; bi[r] = pi; }
+                    else if (s == pos) { bd[r] = dn; bi[r] = in; }
+                }
+                const int wl = (K - 1) & 31;
+                float wsel = bd[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) wsel = ((K - 1) >> 5) == r ? bd[r] : wsel;
+                worst = __shfl_sync(0xffffffffu, wsel, wl);
+            }
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int s = r * 32 + lane;
+        if (s < K) {
+            idx_out[((size_t)b * S + q) * K + s] = bi[r];
+            if (dist_out) dist_out[((size_t)b * S + q) * K + s] = bd[r];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // grouping / gather (+ gradients)
 // ------------------------------------------------------------------------------------------------
@@ -303,6 +410,25 @@ int up3d_subsample_group(int B, int N, int G, int K, float radius, const float *
     ball_query_kernel<true><<<dim3(div_up(G, BQ_WARPS), B), BQ_WARPS * 32, sizeof(int32_t) * BQ_WARPS * K, stream>>>(
         N, G, K, r2, nullptr, xyz, fps_idx, idx, center, neighborhood);
     UP3D_LAUNCH_OK("ball_query_kernel<fused>");
+    return 0;
+}
+
+
+int up3d_knn(int B, int N, int S, int K, int D, const float *xyz, const float *query, int32_t *idx, float *dist,
+             up3d_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    UP3D_CHECK_ARG(B >= 0 && N > 0 && S >= 0 && K > 0, "up3d_knn: bad sizes B=%d N=%d S=%d K=%d", B, N, S, K);
+    UP3D_CHECK_ARG(K <= N, "up3d_knn: K (%d) must not exceed N (%d)", K, N);
+    UP3D_CHECK_ARG(K <= 32 * KNN_MAXR, "up3d_knn: K > %d not supported", 32 * KNN_MAXR);
+    UP3D_CHECK_ARG(D == 3 || D == 4, "up3d_knn: point dimension must be 3 or 4 (got %d)", D);
+    if (B == 0 || S == 0) return 0;
+    UP3D_CHECK_ARG(xyz && query && idx, "up3d_knn: null pointer");
+    const dim3 grid(div_up(S, KNN_WARPS), B);
+    if (K <= 32 && D == 3) knn_kernel<1, 3><<<grid, KNN_WARPS * 32, 0, stream>>>(N, S, K, xyz, query, idx, dist);
+    else if (K <= 32) knn_kernel<1, 4><<<grid, KNN_WARPS * 32, 0, stream>>>(N, S, K, xyz, query, idx, dist);
+    else if (D == 3) knn_kernel<2, 3><<<grid, KNN_WARPS * 32, 0, stream>>>(N, S, K, xyz, query, idx, dist);
+    else knn_kernel<2, 4><<<grid, KNN_WARPS * 32, 0, stream>>>(N, S, K, xyz, query, idx, dist);
+    UP3D_LAUNCH_OK("knn_kernel");
     return 0;
 }
 

@@ -62,10 +62,14 @@ class PointFeaturePredictor(nn.Module):
             self.encoder = PointTransformerEncoder(in_channels=3, num_groups=128, encoder_dims=384, depth=16,
                                                    use_fusion=bool(getattr(cfg.opt, "use_fusion", True)))
             self.final = nn.Sequential(nn.Linear(384, 128), nn.ReLU(), nn.Linear(128, 23))
+        elif model_type == "pointmlp":
+            from .pointmlp import pointMLP
+            self.encoder = pointMLP(cfg=cfg)
+            self.final = nn.Sequential(nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 23))
         else:
             raise NotImplementedError(
-                f"backbone_type={model_type!r}: only 'transformer' (SURVEY.md §8a rows B1-B5) is built; "
-                "pointmlp is row B6, ptv3/sparseunet rows P1/P2 (need spconv), pcm/mamba3d are out of scope")
+                f"backbone_type={model_type!r}: 'transformer' (SURVEY.md §8a rows B1-B5) and 'pointmlp' (row B6) are "
+                "built; ptv3/sparseunet are rows P1/P2 (need a sparse-conv engine), pcm/mamba3d are out of scope")
         if pretrained_path is not None:
             info = self.load_state_dict(torch.load(pretrained_path), strict=False)
             print(f"Loaded pretrained weights from {pretrained_path}")

@@ -141,3 +141,20 @@ def subsample_group(xyz: torch.Tensor, num_groups: int, group_size: int, radius:
     if return_idx:
         return neigh, center, fidx, idx
     return neigh, center
+
+
+def knn_point(nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor, return_dist: bool = False):
+    """pointMLP's knn_point (openpoints/models/backbone/pointmlp.py:102-113): indices of the `nsample` nearest points
+    of `xyz` (B,N,C) for every query in `new_xyz` (B,S,C), C in {3,4}; int64 (B,S,nsample), ascending distance (the
+    reference's order is unspecified: topk(sorted=False)).  No distance matrix is materialised."""
+    require_cuda(xyz, new_xyz)
+    xyz, new_xyz = xyz.contiguous().float(), new_xyz.contiguous().float()
+    B, N, Cd = xyz.shape
+    S = new_xyz.shape[1]
+    with torch.no_grad():
+        idx = torch.empty((B, S, nsample), dtype=torch.int32, device=xyz.device)
+        dist = torch.empty((B, S, nsample), dtype=torch.float32, device=xyz.device) if return_dist else None
+        with torch.cuda.device(xyz.device):
+            check(_lib.lib.up3d_knn(B, N, S, int(nsample), int(Cd), ptr(xyz), ptr(new_xyz), ptr(idx), ptr(dist),
+                                    stream_ptr()), 1)
+    return (idx.long(), dist) if return_dist else idx.long()
