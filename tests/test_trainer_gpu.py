@@ -113,3 +113,24 @@ def test_lazy_image_features_equal_dense_dataflow():
     assert torch.allclose(a, b, atol=2e-5, rtol=1e-5)
     for u, v in zip(ga, gb):
         assert torch.allclose(u, v, atol=1e-4 * float(v.abs().max()) + 1e-6, rtol=1e-4)
+
+
+def test_shadow_bf16_weights_equal_autocast():
+    """Persistent bf16 shadow weights (mixed_precision.py) == torch.autocast numerics, step by step."""
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.trainer import Trainer
+    cfg = _cfg(res=64, bs=2)
+    data = synthetic.make_batch(cfg, 2, 1024, seed=5, pin=True)
+    out = {}
+    for shadow in (False, True):
+        torch.manual_seed(0)
+        tr = Trainer(cfg, use_cuda_graph=False, autocast_dtype=torch.bfloat16, shadow_weights=shadow)
+        for blk in tr.model_manager.model.modules():
+            if blk.__class__.__name__ == "DropPath":
+                blk.drop_prob = 0.0
+        losses = [tr.train_iteration(data) for _ in range(3)]
+        out[shadow] = (losses, [p.detach().clone() for p in tr.params])
+    la, lb = out[False][0], out[True][0]
+    assert abs(la[0] - lb[0]) <= 1e-3 * abs(la[0])              # same forward (bf16 rounding of the same operands)
+    assert abs(la[-1] - lb[-1]) <= 2e-2 * abs(la[-1])
+    assert lb[-1] < lb[0]

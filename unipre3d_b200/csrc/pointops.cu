@@ -4,9 +4,12 @@
 // group_points_gpu.cu} (pybind surface pointnet2_api.cpp:10-24).  Index outputs are bit-identical to the
 // reference kernels, including its tie-breaking (see fps_priority below); the squared distance uses the
 // exact operation order nvcc emits for the reference source: d = fma(dz,dz, fma(dx,dx, dy*dy)).
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace up3d {
 
@@ -103,6 +106,89 @@ fps_resident_kernel(int N, int M, int bs, int log2bs, const float *__restrict__ 
         old = fps_index_from_priority(bl, bs, log2bs);
         if (tid == 0) out[r] = old;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cluster-parallel FPS: one thread-block CLUSTER (8 CTAs = 8 SMs) per cloud instead of one CTA.
+// Each CTA owns a contiguous 1/8 of the points (registers) and a full shared-memory copy of the cloud (query
+// point look-up).  Per round: CTA-local arg-max (REDUX + one __syncthreads) -> 8 lanes push the CTA's candidate
+// into every peer's shared memory through DSMEM -> ONE cluster barrier -> every thread picks the winner of the 8
+// candidates.  Same 64-bit (distance, tie-priority) key as above, so the index sequence is unchanged.
+// ------------------------------------------------------------------------------------------------
+constexpr int FPSC_CLUSTER = 8;
+constexpr int FPSC_THREADS = 512;
+constexpr int FPSC_MAX_PPT = 4;     // N <= 8 * 512 * 4 = 16384
+
+template <int PPT>
+__global__ void __cluster_dims__(FPSC_CLUSTER, 1, 1) __launch_bounds__(FPSC_THREADS, 1)
+fps_cluster_kernel(int N, int M, int bs, int log2bs, const float *__restrict__ xyz, int32_t *__restrict__ idxs) {
+    extern __shared__ float s_pts[];                       // [3][N] full cloud
+    __shared__ uint32_t wred[2][FPSC_THREADS / 32][2];     // warp partials (double-buffered)
+    __shared__ uint32_t cred[2][FPSC_CLUSTER][2];          // one candidate per CTA of the cluster (double-buffered)
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / FPSC_CLUSTER, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *ds = xyz + (size_t)b * N * 3;
+    int32_t *out = idxs + (size_t)b * M;
+    float *sx = s_pts, *sy = s_pts + N, *sz = s_pts + 2 * N;
+    for (int k = tid; k < N; k += FPSC_THREADS) { sx[k] = ds[3 * k]; sy[k] = ds[3 * k + 1]; sz[k] = ds[3 * k + 2]; }
+    const int chunk = (N + FPSC_CLUSTER - 1) / FPSC_CLUSTER;
+    const int k_begin = rank * chunk, k_end = min(N, k_begin + chunk);
+    __syncthreads();
+    float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+    uint32_t pr[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int k = k_begin + tid + j * FPSC_THREADS;
+        const bool valid = k < k_end;
+        px[j] = valid ? sx[k] : 0.f; py[j] = valid ? sy[k] : 0.f; pz[j] = valid ? sz[k] : 0.f;
+        pr[j] = valid ? fps_priority(k, bs, log2bs) : 0u;
+        tmp[j] = 1e10f;
+    }
+    if (rank == 0 && tid == 0) out[0] = 0;
+    // peers' candidate slots for this CTA (lanes 0..7 of warp 0 each own one peer)
+    uint32_t *peer_slot = nullptr;
+    if (warp == 0 && lane < FPSC_CLUSTER) peer_slot = cluster.map_shared_rank(&cred[0][0][0], lane);
+    cluster.sync();
+    int old = 0;
+    for (int r = 1; r < M; ++r) {
+        const int buf = r & 1;
+        const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+        uint32_t bh = 0u, bl = 0u;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float dx = xsub(px[j], x1), dy = xsub(py[j], y1), dz = xsub(pz[j], z1);
+            const float d = xfma(dz, dz, xfma(dx, dx, xmul(dy, dy)));
+            const float d2 = fminf(d, tmp[j]);
+            tmp[j] = d2;
+            const uint32_t h = __float_as_uint(d2);
+            const bool better = pr[j] != 0u && (h > bh || (h == bh && pr[j] > bl));
+            bh = better ? h : bh;
+            bl = better ? pr[j] : bl;
+        }
+        uint32_t mh = __reduce_max_sync(0xffffffffu, bh);
+        uint32_t ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
+        if (lane == 0) { wred[buf][warp][0] = mh; wred[buf][warp][1] = ml; }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t h2 = lane < FPSC_THREADS / 32 ? wred[buf][lane][0] : 0u;
+            const uint32_t l2 = lane < FPSC_THREADS / 32 ? wred[buf][lane][1] : 0u;
+            mh = __reduce_max_sync(0xffffffffu, h2);
+            ml = __reduce_max_sync(0xffffffffu, h2 == mh ? l2 : 0u);
+            if (lane < FPSC_CLUSTER) {      // DSMEM: write this CTA's candidate into peer `lane`
+                uint32_t *dst = peer_slot + (buf * FPSC_CLUSTER + rank) * 2;
+                dst[0] = mh; dst[1] = ml;
+            }
+        }
+        cluster.sync();                     // release/acquire: all 8 candidates visible everywhere
+        const uint32_t h3 = lane < FPSC_CLUSTER ? cred[buf][lane][0] : 0u;
+        const uint32_t l3 = lane < FPSC_CLUSTER ? cred[buf][lane][1] : 0u;
+        mh = __reduce_max_sync(0xffffffffu, h3);
+        ml = __reduce_max_sync(0xffffffffu, h3 == mh ? l3 : 0u);
+        old = fps_index_from_priority(ml, bs, log2bs);
+        if (rank == 0 && tid == 0) out[r] = old;
+    }
+    cluster.sync();                         // no CTA may exit while peers can still write into its shared memory
 }
 
 // streaming fallback for clouds that do not fit the register file: temp lives in global memory
@@ -362,7 +448,21 @@ int up3d_fps(int B, int N, int M, const float *xyz, float *temp, int32_t *idx, u
     const int bs = ref_block_size(N);
     int log2bs = 0;
     while ((1 << log2bs) < bs) ++log2bs;
-    if (N <= FPS_THREADS * FPS_MAX_PPT) {
+    if (N > 4096 && N <= FPSC_CLUSTER * FPSC_THREADS * FPSC_MAX_PPT && M >= 32) {   // measured: the cluster barrier only pays off above 4096 points
+        // one 8-CTA cluster per cloud (DSMEM candidate exchange)
+        const size_t smem = sizeof(float) * 3 * (size_t)N;
+        const int ppt = div_up(div_up(N, FPSC_CLUSTER), FPSC_THREADS);
+#define UP3D_FPSC_CASE(P)                                                                                          \
+    {                                                                                                              \
+        UP3D_CUDA_OK(cudaFuncSetAttribute(fps_cluster_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fps_cluster_kernel<P><<<B * FPSC_CLUSTER, FPSC_THREADS, smem, stream>>>(N, M, bs, log2bs, xyz, idx);        \
+    }
+        if (ppt <= 1) UP3D_FPSC_CASE(1)
+        else if (ppt <= 2) UP3D_FPSC_CASE(2)
+        else UP3D_FPSC_CASE(4)
+#undef UP3D_FPSC_CASE
+        UP3D_LAUNCH_OK("fps_cluster_kernel");
+    } else if (N <= FPS_THREADS * FPS_MAX_PPT) {
         const size_t smem = sizeof(float) * 3 * (size_t)N;
 #define UP3D_FPS_CASE(P)                                                                                           \
     {                                                                                                              \

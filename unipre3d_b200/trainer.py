@@ -176,7 +176,7 @@ class Trainer:
     """Step driver.  `train_iteration(data)` == reference 450-464 + 333-352 for one batch dict (host tensors)."""
 
     def __init__(self, cfg, device: Optional[torch.device] = None, use_cuda_graph: bool = False,
-                 autocast_dtype: Optional[torch.dtype] = None):
+                 autocast_dtype: Optional[torch.dtype] = None, shadow_weights: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("unipre3d_b200.Trainer needs a CUDA device (there is no CPU fallback)")
         self.cfg = cfg
@@ -190,6 +190,10 @@ class Trainer:
         self.model_manager = ModelManager(cfg, self.device, capturable=use_cuda_graph)
         self.validation_manager = ValidationManager(cfg, self.device)
         self.params = [p for p in self.model_manager.model.parameters() if p.requires_grad]
+        self._shadow = None
+        if autocast_dtype == torch.bfloat16 and shadow_weights:
+            from .mixed_precision import ShadowWeights
+            self._shadow = ShadowWeights(self.model_manager.model)
         self.found_inf = torch.zeros((), dtype=torch.float32, device=self.device)
         self.model_manager.optimizer.grad_scale = None
         self.model_manager.optimizer.found_inf = self.found_inf
@@ -265,6 +269,8 @@ class Trainer:
         coef = torch.where(torch.isfinite(coef), coef, torch.zeros_like(coef))
         torch._foreach_mul_(grads, coef)
         mm.optimizer.step()
+        if self._shadow is not None:
+            self._shadow.refresh()            # one multi-tensor fp32 -> bf16 copy for all Linear layers
         mm.optimizer.zero_grad(set_to_none=True)   # grads are re-materialised at the same graph-pool addresses on replay
 
     def _step_body(self, data) -> torch.Tensor:
