@@ -488,39 +488,90 @@ __device__ __forceinline__ float gauss_power(const float4 co, float dx, float dy
     return xfma(-0.5f, A, -xmul(xmul(co.y, dx), dy));
 }
 
-struct TileChunk {  // one 256-record chunk compacted to the entries covering this tile
+// ---- TMA (bulk async copy) + mbarrier helpers: cp.async.bulk global -> shared, completion on an mbarrier -------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+// One 256-record chunk of a view's depth-ordered records, staged in shared memory exactly as it lies in HBM
+// (five contiguous slices -> five bulk copies on one mbarrier), then compacted IN PLACE to the entries whose
+// rectangle covers this tile (order preserved).  In the reference's regime every record covers every tile, the
+// compaction is the identity and the staged chunk is consumed as is.
+struct __align__(128) StageBuf {
     float2 xy[UP3D_TILE_PIX];
     float4 co[UP3D_TILE_PIX];
     float4 rgb[UP3D_TILE_PIX];
     int32_t id[UP3D_TILE_PIX];
-    int warp_cnt[8];
+    uint32_t rect[UP3D_TILE_PIX];
 };
 
-// Loads records [base, base+256) of the view, keeps those whose rect covers tile (tx,ty), in order.
-// Returns the number kept.  All 256 threads must call.  Two __syncthreads inside.
+// thread 0 only: arm the barrier and launch the bulk copies of records [base, base + rows) (rows rounded up to 4 so
+// every slice is a multiple of 16 bytes; the over-read stays inside the state blob and is never consumed)
 template <bool WITH_ID>
-__device__ __forceinline__ int load_compact_chunk(TileChunk &ch, const State &st, int rec0, int n, int base, int tx,
-                                                  int ty) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = base + tid;
-    bool hit = false;
-    if (k < n) hit = rect_covers(st.s_rect[rec0 + k], tx, ty);
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) ch.warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int off = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const int c = ch.warp_cnt[w];
-        off += (w < warp) ? c : 0;
-        total += c;
+__device__ __forceinline__ void stage_issue(StageBuf &sb, uint64_t *bar, const State &st, int rec0, int n, int base) {
+    const int rows = min(UP3D_TILE_PIX, n - base);
+    const uint32_t r4 = (uint32_t)((rows + 3) & ~3);
+    fence_proxy_async();   // earlier generic-proxy accesses to this buffer are ordered before the async-proxy writes
+    mbar_expect_tx(bar, r4 * (8u + 16u + 16u + 4u + (WITH_ID ? 4u : 0u)));
+    const size_t o = (size_t)rec0 + base;
+    bulk_g2s(sb.xy, st.s_xy + o, r4 * 8u, bar);
+    bulk_g2s(sb.co, st.s_co + o, r4 * 16u, bar);
+    bulk_g2s(sb.rgb, st.s_rgb + o, r4 * 16u, bar);
+    bulk_g2s(sb.rect, st.s_rect + o, r4 * 4u, bar);
+    if (WITH_ID) bulk_g2s(sb.id, st.s_id + o, r4 * 4u, bar);
+}
+
+// fallback when the view's record range is not 16-byte aligned for every slice: plain coalesced loads
+template <bool WITH_ID>
+__device__ __forceinline__ void stage_fill_plain(StageBuf &sb, const State &st, int rec0, int n, int base) {
+    const int tid = threadIdx.x, k = base + tid;
+    if (k < n) {
+        sb.xy[tid] = st.s_xy[rec0 + k];
+        sb.co[tid] = st.s_co[rec0 + k];
+        sb.rgb[tid] = st.s_rgb[rec0 + k];
+        sb.rect[tid] = st.s_rect[rec0 + k];
+        if (WITH_ID) sb.id[tid] = st.s_id[rec0 + k];
     }
+}
+
+// In-place ordered compaction of a staged chunk to the records covering tile (tx, ty).  Returns the number kept.
+// All 256 threads call; the staged data must be visible (mbarrier wait / __syncthreads) to all of them.
+template <bool WITH_ID>
+__device__ __forceinline__ int stage_compact(StageBuf &sb, int *warp_cnt, int n, int base, int tx, int ty) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows = min(UP3D_TILE_PIX, n - base);
+    const bool hit = tid < rows && rect_covers(sb.rect[tid], tx, ty);
+    const int total = __syncthreads_count(hit);
+    if (total == rows) return total;           // dense: identity
+    float2 xy; float4 co, rgb; int32_t id = 0;
+    if (hit) { xy = sb.xy[tid]; co = sb.co[tid]; rgb = sb.rgb[tid]; if (WITH_ID) id = sb.id[tid]; }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();                            // all reads done, warp counts visible
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) off += (w < warp) ? warp_cnt[w] : 0;
     if (hit) {
         const int slot = off + __popc(bal & lanemask_lt());
-        ch.xy[slot] = st.s_xy[rec0 + k];
-        ch.co[slot] = st.s_co[rec0 + k];
-        ch.rgb[slot] = st.s_rgb[rec0 + k];
-        if (WITH_ID) ch.id[slot] = st.s_id[rec0 + k];
+        sb.xy[slot] = xy; sb.co[slot] = co; sb.rgb[slot] = rgb;
+        if (WITH_ID) sb.id[slot] = id;
     }
     __syncthreads();
     return total;
@@ -536,7 +587,9 @@ struct BlendArgs {
 };
 
 __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_forward_kernel(const BlendArgs a) {
-    __shared__ TileChunk ch;
+    __shared__ StageBuf stage[2];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int warp_cnt[8];
     const int v = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
     const int tid = threadIdx.x;
     const int px = tx * UP3D_TILE + (tid & 15), py = ty * UP3D_TILE + (tid >> 4);
@@ -544,16 +597,36 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_forward_kernel(const Blen
     const int rec0 = a.view_rec_start[v];
     const int n = a.st.n_vis[v];
     const float pfx = (float)px, pfy = (float)py;
+    const bool tma = (rec0 & 3) == 0;          // every slice of the view's records starts 16-byte aligned
+    const int nchunks = (n + UP3D_TILE_PIX - 1) / UP3D_TILE_PIX;
+    if (tma && tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    __syncthreads();
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, ID = 0.f;
     int contributor = 0, last_contributor = 0;
-    for (int base = 0; base < n; base += UP3D_TILE_PIX) {
-        if (__syncthreads_count(done) == UP3D_TILE_PIX) break;
-        const int cnt = load_compact_chunk<false>(ch, a.st, rec0, n, base, tx, ty);
+    int issued = 0;                              // chunks whose bulk copy has been launched (block-uniform)
+    int c = 0;
+    for (; c < nchunks; ++c) {
+        // everyone finished reading the buffers of chunk c-1 (and c-2) once this barrier is passed
+        if (c > 0 && __syncthreads_count(done) == UP3D_TILE_PIX) break;
+        StageBuf &sb = stage[c & 1];
+        if (tma) {
+            if (issued == c) { if (tid == 0) stage_issue<false>(sb, &bar[c & 1], a.st, rec0, n, c * UP3D_TILE_PIX); issued = c + 1; }
+            // prefetch the next chunk only for tiles that already proved to need more than one
+            if (c >= 1 && c + 1 < nchunks && issued == c + 1) {
+                if (tid == 0) stage_issue<false>(stage[(c + 1) & 1], &bar[(c + 1) & 1], a.st, rec0, n, (c + 1) * UP3D_TILE_PIX);
+                issued = c + 2;
+            }
+            mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
+        } else {
+            stage_fill_plain<false>(sb, a.st, rec0, n, c * UP3D_TILE_PIX);
+            __syncthreads();
+        }
+        const int cnt = stage_compact<false>(sb, warp_cnt, n, c * UP3D_TILE_PIX, tx, ty);
         for (int j = 0; !done && j < cnt; ++j) {
             contributor++;
-            const float2 xy = ch.xy[j];
-            const float4 co = ch.co[j];
+            const float2 xy = sb.xy[j];
+            const float4 co = sb.co[j];
             const float dx = xy.x - pfx, dy = xy.y - pfy;
             const float power = gauss_power(co, dx, dy);
             if (power > 0.0f) continue;
@@ -561,13 +634,15 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_forward_kernel(const Blen
             if (alpha < 1.0f / 255.0f) continue;
             const float test_T = T * (1.f - alpha);
             if (test_T < 0.0001f) { done = true; continue; }
-            const float4 c = ch.rgb[j];
+            const float4 col = sb.rgb[j];
             const float wgt = alpha * T;
-            C0 += c.x * wgt; C1 += c.y * wgt; C2 += c.z * wgt; ID += c.w * wgt;
+            C0 += col.x * wgt; C1 += col.y * wgt; C2 += col.z * wgt; ID += col.w * wgt;
             T = test_T;
             last_contributor = contributor;
         }
     }
+    // a prefetched chunk may still be in flight: it must land before this CTA's shared memory is released
+    if (tma && issued > c && c < nchunks) mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
     if (inside) {
         const size_t HW = (size_t)a.W * a.H, pix = (size_t)py * a.W + px;
         a.st.final_T[v * HW + pix] = T;
@@ -605,7 +680,9 @@ constexpr int BWD_EB = 16;            // entries per sub-batch
 constexpr int BWD_ROW = 256 + 16;     // padded row of the u / w staging arrays (conflict-free phase-2 reads)
 
 struct BwdSmem {
-    TileChunk ch;
+    StageBuf ch;                       // staged + in-place compacted chunk (single buffer: see kernel comment)
+    uint64_t bar;
+    int warp_cnt[8];
     float u[BWD_EB][BWD_ROW];
     float w[BWD_EB][BWD_ROW];
     float dL[3][UP3D_TILE_PIX];
@@ -615,7 +692,7 @@ struct BwdSmem {
 __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const BlendBwdArgs a) {
     extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(bwd_smem_raw);
-    TileChunk &ch = sm.ch;
+    StageBuf &ch = sm.ch;
     const int v = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = tx * UP3D_TILE + (tid & 15), py = ty * UP3D_TILE + (tid >> 4);
@@ -627,6 +704,8 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
 
     const float T_final = inside ? a.st.final_T[v * HW + pix] : 0.f;
     const int last_contributor = inside ? a.st.n_contrib[v * HW + pix] : 0;
+    const bool tma = (rec0 & 3) == 0;
+    if (tma && tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
     int m = __reduce_max_sync(0xffffffffu, last_contributor);
     if (lane == 0) sm.red[warp] = m;
     __syncthreads();
@@ -661,8 +740,20 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
     // phase-2 role of this thread: entry slot e2 of the sub-batch, 16 pixels {part + 16 i}
     const int e2 = tid >> 4, part = tid & 15;
 
+    // Chunks are visited back to front.  In the reference's regime the first Lmax entries live in chunk 0, so a second
+    // staging buffer would only cost occupancy (4 -> 3 CTAs/SM); one buffer, refilled by TMA after the barrier that
+    // ends the previous chunk.
+    uint32_t loads = 0;
     for (int c = c_last; c >= 0; --c) {
-        const int cnt = load_compact_chunk<true>(ch, a.st, rec0, n, c * UP3D_TILE_PIX, tx, ty);  // syncs inside
+        if (tma) {
+            if (tid == 0) stage_issue<true>(ch, &sm.bar, a.st, rec0, n, c * UP3D_TILE_PIX);
+            mbar_wait(&sm.bar, loads & 1u);
+            ++loads;
+        } else {
+            stage_fill_plain<true>(ch, a.st, rec0, n, c * UP3D_TILE_PIX);
+            __syncthreads();
+        }
+        const int cnt = stage_compact<true>(ch, sm.warp_cnt, n, c * UP3D_TILE_PIX, tx, ty);
         const int pos_base = running_end - cnt;  // 0-based list position of entry 0 of this chunk
         running_end = pos_base;
         int jtop = min(cnt - 1, Lmax - 1 - pos_base);   // entries beyond the tile's max n_contrib never contribute
