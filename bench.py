@@ -183,11 +183,7 @@ def raster_roofline(trainer, batch_dev, cfg, reps: int, peaks, peak_kind):
     buf = (C.c_float * 6)()
     try:
         for r in range(reps):
-            model.train()
-            splats = model(**prepare_model_inputs(batch_dev, cfg, OBJECTS_PER_GPU, trainer.device))
-            rendered, gt = trainer.render_validation_views(splats, batch_dev)
-            loss = trainer.validation_manager.calculate_losses(rendered, gt, 0)["total_loss"]
-            loss.backward()
+            trainer._forward_backward(batch_dev)          # eager forward + render + loss + backward (autocast as the step)
             _lib.check(_lib.lib.up3d_raster_timing_read(buf))
             ms[r] = list(buf)
             for p in trainer.params:
@@ -197,7 +193,7 @@ def raster_roofline(trainer, batch_dev, cfg, reps: int, peaks, peak_kind):
     names = ["project", "depth_sort", "blend_forward", "grad_clear", "blend_backward", "geometry_backward"]
     mean = ms.mean(0)
     V = OBJECTS_PER_GPU * int(cfg.opt.imgs_per_obj)
-    P, HW, M = int(splats["xyz"].shape[1]), RES * RES, 4
+    P, HW, M = 128 * int(cfg.data.input_images), RES * RES, 4     # Gaussians per object: 128 tokens x input views
     # algorithmic bytes of blend_backward per launch (DESIGN.md "Kernels"): depth-ordered records read once per view
     # (48 B each), per-pixel final_T / n_contrib / dL_dcolor (20 B), per-record 9-float partials read-modify-write
     bwd_bytes = V * (P * 48 + HW * 20 + P * 9 * 4 * 2)

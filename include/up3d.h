@@ -183,6 +183,59 @@ UP3D_API int up3d_focal_l2_loss(int64_t n_images, int H, int W, const float *ren
                        float non_bg_rate, float bg_rate, float *loss_out, float *dL_drendered,
                        up3d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Transformer-encoder glue (openpoints/models/backbone/transformer.py:89-121 Block, 123-207
+ * TransformerEncoder, 10-33 Mlp): everything between two GEMMs of a Block in ONE pass.
+ * Rows are tokens: T = B*L rows of width C (C = 128*{1,2,3,4,6,8}); row r belongs to sample r / L.
+ * act_bf16 selects the dtype of the GEMM-side activations (0: float, 1: __nv_bfloat16); the
+ * residual stream, LayerNorm statistics and every parameter gradient are fp32.
+ * ---------------------------------------------------------------------------------------- */
+
+/* xs = x + scale[r/L]*delta + pos  (delta, scale, pos optional; scale NULL == 1: DropPath's per-sample
+ * keep/(1-p) factor, transformer.py:119-120; pos: `block(x + pos)`, transformer.py:188);
+ * y = LayerNorm(xs; gamma, beta, eps) (nn.LayerNorm semantics, biased variance); mean/rstd (T) saved for
+ * the backward.  xs_out may be NULL; y may be NULL (then only the residual sum is written). */
+UP3D_API int up3d_ln_fwd(int act_bf16, int T, int L, int C, const float *x, const void *delta, const float *scale,
+                         const float *pos, const float *gamma, const float *beta, float eps, float *xs_out, void *y,
+                         float *mean, float *rstd, up3d_stream_t stream);
+
+/* dx = g_res + dLayerNorm(dy)  (g_res optional: the gradient arriving on the residual path);
+ * dgamma/dbeta (C) += column sums (atomic accumulate: zero them once per step);
+ * dpos (T,C) += dx when not NULL; dscaled (T,C, activation dtype) = scale[r/L]*dx when not NULL --
+ * the dY of the Linear that produced the residual branch in front of this LayerNorm -- and
+ * dbias (C) += column sums of dscaled (that Linear's bias gradient). */
+UP3D_API int up3d_ln_bwd(int act_bf16, int T, int L, int C, const void *dy, const float *xs, const float *mean,
+                         const float *rstd, const float *gamma, const float *g_res, const float *scale, float *dx,
+                         float *dpos, void *dscaled, float *dgamma, float *dbeta, float *dbias, up3d_stream_t stream);
+
+/* y = GELU(x), erf form (nn.GELU default, transformer.py:17), n elements (multiple of 4). */
+UP3D_API int up3d_gelu_fwd(int act_bf16, int64_t n, const void *x, void *y, up3d_stream_t stream);
+/* dx = dy * GELU'(pre) over (T,C); dbias (C, may be NULL) += column sums of dx (fc1's bias gradient). */
+UP3D_API int up3d_gelu_bwd(int act_bf16, int T, int C, const void *dy, const void *pre, void *dx, float *dbias,
+                           up3d_stream_t stream);
+/* out (T,C, activation dtype) = scale[r/L] * g (fp32); dbias (C, may be NULL) += column sums of out. */
+UP3D_API int up3d_scale_cast_colsum(int act_bf16, int T, int L, int C, const float *g, const float *scale, void *out,
+                                    float *dbias, up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step of train_network.py:333-352: `_check_and_clip_gradients` (368-390: skip the step when any
+ * gradient is NaN/Inf, else clip_grad_norm_(max_norm=1.0)) + torch.optim.AdamW(eps=1e-15) (156-159) in three
+ * launches over a multi-tensor work list: sum of squares -> (coef, found_inf) -> one read-modify-write pass
+ * over param / exp_avg / exp_avg_sq (+ optional bf16 shadow of the new parameter values).
+ *   work list: chunk c covers tensor chunk_tensor[c], elements [chunk_start[c], +up3d_adamw_chunk_elems());
+ *   pointer tables (device arrays of device pointers, n_tensors each); bf16_shadows[i] may be NULL, and the
+ *   table itself may be NULL; group[i] indexes lrs (device floats, so a captured CUDA graph sees LR changes).
+ *   state: 8-byte aligned device buffer of 24 bytes, zero-initialised once:
+ *          fp64 sum-of-squares accumulator | float step | float total_norm | float clip_coef | float found_inf.
+ * A non-finite total norm leaves parameters, moments and the step counter untouched.
+ * ---------------------------------------------------------------------------------------- */
+UP3D_API int up3d_adamw_chunk_elems(void);
+UP3D_API int up3d_adamw_step(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
+                             const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
+                             float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
+                             float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
+                             up3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

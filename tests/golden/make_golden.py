@@ -241,6 +241,44 @@ def main():
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 
+def blocks_only():
+    """transformer_blocks_w128.npz : openpoints/models/backbone/transformer.py TransformerEncoder (the Block stack alone,
+    width 128 so that the CUDA fused stack -- width a multiple of 128 -- is pinned against the reference module)."""
+    stub("timm"); stub("timm.models")
+    stub("timm.models.layers", DropPath=_DropPath, trunc_normal_=torch.nn.init.trunc_normal_)
+    stub("openpoints"); stub("openpoints.models")
+    stub("openpoints.models.build", MODELS=_Registry())
+    stub("openpoints.models.layers", SubsampleGroup=_FixedGroups)
+    stub("fusion", FeatureFusion=object)
+    tr = load("ref_transformer", os.path.join(REF, "openpoints/models/backbone/transformer.py"))
+    torch.manual_seed(11)
+    B, L, C, depth, heads = 3, 17, 128, 2, 4
+    enc = tr.TransformerEncoder(embed_dim=C, depth=depth, num_heads=heads, drop_path_rate=[0.0, 0.1])
+    with torch.no_grad():
+        for q in enc.parameters():
+            if q.ndim == 1:
+                q.add_(torch.randn_like(q) * 0.2)     # non-trivial LayerNorm affine parameters and biases
+    enc.train()
+    for m in enc.modules():
+        if isinstance(m, _DropPath):
+            m.drop_prob = 0.0
+    x = torch.randn(B, L, C, requires_grad=True)
+    pos = (torch.randn(B, L, C) * 0.3).requires_grad_(True)
+    out = enc(x, pos, None, None, None, None, None)
+    wsum = torch.randn_like(out)
+    (out * wsum).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "transformer_blocks_w128.npz"), cfg=np.array([B, L, C, depth, heads]),
+                        x=x.detach().numpy(), pos=pos.detach().numpy(), wsum=wsum.numpy(), out=out.detach().numpy(),
+                        grad_x=x.grad.numpy(), grad_pos=pos.grad.numpy(),
+                        **{"sd." + k: v.detach().numpy() for k, v in enc.state_dict().items()},
+                        **{"grad." + k: q.grad.numpy() for k, q in enc.named_parameters()})
+    print("wrote transformer_blocks_w128.npz")
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "blocks":
+        blocks_only()
+    else:
+        main()
+        blocks_only()

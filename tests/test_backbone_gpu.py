@@ -1,0 +1,285 @@
+"""Fused transformer glue + optimizer kernels (csrc/backbone.cu) against plain PyTorch fp32 references of the same
+ops, the fused 16-block stack against the module loop that mirrors the reference (backbone.py), and against the golden
+fixture generated from the reference's own PointTransformerEncoder (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda"
+
+
+def _tol(act):
+    # bf16 outputs carry one rounding of a value of magnitude ~|x| (2^-9 relative)
+    return dict(atol=2e-5, rtol=1e-5) if act == torch.float32 else dict(atol=2e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("act", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [128, 384, 768])
+def test_ln_fwd_matches_torch(act, C):
+    from unipre3d_b200 import fused_encoder as fe
+    torch.manual_seed(0)
+    B, L = 3, 37
+    T = B * L
+    x = torch.randn(T, C, device=DEV)
+    delta = torch.randn(T, C, device=DEV).to(act)
+    pos = torch.randn(T, C, device=DEV)
+    scale = torch.tensor([0.0, 1.25, 1.0], device=DEV)
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    xs, y, mean, rstd = fe.ln_fwd(x, delta, scale, pos, gamma, beta, 1e-5, L, act)
+    xs_ref = x + scale.repeat_interleave(L).unsqueeze(1) * delta.float() + pos
+    y_ref = F.layer_norm(xs_ref, (C,), gamma, beta, 1e-5)
+    assert torch.allclose(xs, xs_ref, atol=1e-6, rtol=1e-6)
+    assert torch.allclose(y.float(), y_ref, **_tol(act))
+    assert torch.allclose(mean, xs_ref.mean(1), atol=1e-5)
+    assert torch.allclose(rstd, (xs_ref.var(1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-5)
+    # optional inputs absent: plain LayerNorm; residual-only mode
+    _, y2, _, _ = fe.ln_fwd(x, None, None, None, gamma, beta, 1e-5, L, act, want_xs=False)
+    assert torch.allclose(y2.float(), F.layer_norm(x, (C,), gamma, beta, 1e-5), **_tol(act))
+    xs3, y3, _, _ = fe.ln_fwd(x, delta, scale, None, None, None, 0.0, L, act, want_y=False)
+    assert y3 is None and torch.allclose(xs3, x + scale.repeat_interleave(L).unsqueeze(1) * delta.float(), atol=1e-6)
+
+
+@pytest.mark.parametrize("act", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [128, 384])
+def test_ln_bwd_matches_torch_autograd(act, C):
+    from unipre3d_b200 import fused_encoder as fe
+    torch.manual_seed(1)
+    B, L = 5, 129
+    T = B * L
+    xs = torch.randn(T, C, device=DEV, requires_grad=True)
+    gamma = (torch.rand(C, device=DEV) + 0.5).requires_grad_(True)
+    beta = torch.randn(C, device=DEV, requires_grad=True)
+    dy = torch.randn(T, C, device=DEV).to(act)
+    g_res = torch.randn(T, C, device=DEV)
+    scale = torch.tensor([0.0, 1.1, 1.0, 1.1, 0.0], device=DEV)
+    y = F.layer_norm(xs, (C,), gamma, beta, 1e-5)
+    dxs_ref, dg_ref, db_ref = torch.autograd.grad(y, [xs, gamma, beta], dy.float())
+    dx_ref = g_res + dxs_ref
+    with torch.no_grad():
+        mean = xs.mean(1)
+        rstd = (xs.var(1, unbiased=False) + 1e-5).rsqrt()
+        dpos = torch.full((T, C), 0.5, device=DEV)
+        dgamma, dbeta, dbias = (torch.zeros(C, device=DEV) for _ in range(3))
+        dx, dsc = fe.ln_bwd(dy, xs.detach(), mean, rstd, gamma.detach(), g_res, scale, L, dpos, True, dgamma, dbeta, dbias)
+    tol = dict(atol=1e-4, rtol=1e-4)
+    assert torch.allclose(dx, dx_ref, **tol)
+    assert torch.allclose(dpos, 0.5 + dx_ref, **tol)
+    sc_ref = scale.repeat_interleave(L).unsqueeze(1) * dx_ref
+    assert torch.allclose(dsc.float(), sc_ref, **_tol(act))
+    assert torch.allclose(dgamma, dg_ref, atol=2e-3, rtol=1e-3)
+    assert torch.allclose(dbeta, db_ref, atol=2e-3, rtol=1e-3)
+    assert torch.allclose(dbias, dsc.float().sum(0), atol=2e-3, rtol=1e-3)
+    # no residual / no scaled output
+    with torch.no_grad():
+        dgamma.zero_(); dbeta.zero_()
+        dx2, none = fe.ln_bwd(dy, xs.detach(), mean, rstd, gamma.detach(), None, None, L, None, False, dgamma, dbeta, None)
+    assert none is None and torch.allclose(dx2, dxs_ref, **tol)
+
+
+@pytest.mark.parametrize("act", [torch.float32, torch.bfloat16])
+def test_gelu_and_colsum_kernels_match_torch(act):
+    from unipre3d_b200 import fused_encoder as fe
+    torch.manual_seed(2)
+    T, C, L = 1032, 1536, 129
+    pre = (torch.randn(T, C, device=DEV) * 2).to(act)
+    dy = torch.randn(T, C, device=DEV).to(act)
+    h = fe.gelu_fwd(pre)
+    assert torch.allclose(h.float(), F.gelu(pre.float()), **_tol(act))
+    p32 = pre.float().requires_grad_(True)
+    (dref,) = torch.autograd.grad(F.gelu(p32), p32, dy.float())
+    db = torch.zeros(C, device=DEV)
+    dx = fe.gelu_bwd(dy, pre, db)
+    assert torch.allclose(dx.float(), dref, **_tol(act))
+    assert torch.allclose(db, dx.float().sum(0), atol=5e-3, rtol=1e-3)
+    g = torch.randn(T, 384, device=DEV)
+    scale = torch.rand(T // L, device=DEV)
+    db2 = torch.zeros(384, device=DEV)
+    out = fe.scale_cast_colsum(g, scale, L, act, db2)
+    ref = scale.repeat_interleave(L).unsqueeze(1) * g
+    assert torch.allclose(out.float(), ref, **_tol(act))
+    assert torch.allclose(db2, out.float().sum(0), atol=5e-3, rtol=1e-3)
+
+
+def _make_blocks(C=384, depth=4, heads=6, dpr=0.1):
+    from unipre3d_b200.backbone import TransformerEncoder
+    torch.manual_seed(3)
+    rates = [x.item() for x in torch.linspace(0, dpr, depth)]
+    enc = TransformerEncoder(embed_dim=C, depth=depth, num_heads=heads, drop_path_rate=rates).to(DEV)
+    with torch.no_grad():
+        for p in enc.parameters():            # non-trivial LayerNorm affine parameters and biases
+            if p.ndim == 1:
+                p.add_(torch.randn_like(p) * 0.1)
+    return enc
+
+
+def _module_loop_with_masks(enc, x, pos, masks):
+    """backbone.Block arithmetic with explicit DropPath factors (transformer.py:119-120, 188)."""
+    for i, blk in enumerate(enc.blocks):
+        x = x + pos
+        s1 = 1.0 if masks is None else masks[2 * i].view(-1, 1, 1)
+        s2 = 1.0 if masks is None else masks[2 * i + 1].view(-1, 1, 1)
+        x = x + s1 * blk.attn(blk.norm1(x))
+        x = x + s2 * blk.mlp(blk.norm2(x))
+    return x
+
+
+@pytest.mark.parametrize("with_masks", [False, True])
+def test_fused_stack_equals_module_loop_fp32(with_masks):
+    from unipre3d_b200 import fused_encoder as fe
+    enc = _make_blocks()
+    assert fe.supports(enc.blocks)
+    B, L, C = 4, 129, 384
+    torch.manual_seed(4)
+    x = torch.randn(B, L, C, device=DEV, requires_grad=True)
+    pos = torch.randn(B, L, C, device=DEV, requires_grad=True)
+    w = torch.randn(B, L, C, device=DEV)
+    masks = None
+    if with_masks:
+        masks = (torch.rand(2 * len(enc.blocks), B, device=DEV) < 0.7).float() / 0.7
+    params = list(enc.parameters())
+    ref = _module_loop_with_masks(enc, x, pos, masks)
+    g_ref = torch.autograd.grad((ref * w).sum(), [x, pos] + params)
+    # fused: same masks injected through the Function directly
+    plist, cw, e1, e2 = [], [], [], []
+    for b in enc.blocks:
+        plist += [b.norm1.weight, b.norm1.bias, b.attn.qkv.weight, b.attn.proj.weight, b.attn.proj.bias, b.norm2.weight,
+                  b.norm2.bias, b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias]
+        cw.append((b.attn.qkv.weight.detach(), b.attn.proj.weight.detach(), b.attn.proj.bias.detach(),
+                   b.mlp.fc1.weight.detach(), b.mlp.fc1.bias.detach(), b.mlp.fc2.weight.detach(), b.mlp.fc2.bias.detach()))
+        e1.append(b.norm1.eps); e2.append(b.norm2.eps)
+    meta = fe._Meta(B, L, C, enc.blocks[0].attn.num_heads, float(enc.blocks[0].attn.scale), e1, e2, torch.float32, cw)
+    out = fe.EncoderStackFn.apply(x, pos, masks, meta, *plist)
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), float((out - ref).abs().max())
+    g = torch.autograd.grad((out * w).sum(), [x, pos] + plist)
+    by_id = {id(p): gi for p, gi in zip([x, pos] + plist, g)}
+    for p, gr in zip([x, pos] + params, g_ref):
+        got = by_id[id(p)]
+        scale = float(gr.abs().max()) + 1e-6
+        assert float((got - gr).abs().max()) <= 2e-3 * scale, (tuple(p.shape), float((got - gr).abs().max()), scale)
+
+
+def test_fused_stack_bf16_close_to_fp32_and_module_dispatch():
+    """TransformerEncoder.forward dispatches to the fused stack on CUDA; under bf16 autocast it stays close to fp32."""
+    enc = _make_blocks(depth=3, dpr=0.0)
+    B, L, C = 2, 129, 384
+    torch.manual_seed(5)
+    x = torch.randn(B, L, C, device=DEV)
+    pos = torch.randn(B, L, C, device=DEV) * 0.1
+    enc.train()
+    a = enc(x, pos, None, None, None, None, None)
+    enc.force_module_path = True
+    b = enc(x, pos, None, None, None, None, None)
+    enc.force_module_path = False
+    assert torch.allclose(a, b, atol=2e-4, rtol=1e-4)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        c = enc(x, pos, None, None, None, None, None)
+    assert c.dtype == torch.float32
+    assert float((c - a).abs().max()) <= 0.05 * float(a.abs().max())
+    (c * c).mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.dtype == torch.float32
+               for p in enc.parameters())
+
+
+def test_fused_stack_matches_reference_module_fixture():
+    """The reference's own TransformerEncoder (Block stack, width 128) output and gradients -- fixture generated by
+    tests/golden/make_golden.py from /root/reference -- through the CUDA fused stack (fp32 operands)."""
+    from tests.test_golden_cpu import _blocks_from_fixture
+    from unipre3d_b200 import fused_encoder as fe
+    z = np.load(os.path.join(G, "transformer_blocks_w128.npz"))
+    enc = _blocks_from_fixture(z).to(DEV)
+    assert fe.supports(enc.blocks)
+    x = torch.tensor(z["x"], device=DEV, requires_grad=True)
+    pos = torch.tensor(z["pos"], device=DEV, requires_grad=True)
+    enc.train()
+    for m in enc.modules():
+        if m.__class__.__name__ == "DropPath":
+            m.drop_prob = 0.0
+    before = _lib_launches()
+    out = enc(x, pos, None, None, None, None, None)
+    assert _lib_launches() > before, "the fused CUDA stack did not run"
+    np.testing.assert_allclose(out.detach().cpu().numpy(), z["out"], atol=5e-5, rtol=1e-4)
+    (out * torch.tensor(z["wsum"], device=DEV)).sum().backward()
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    checks = [("grad_x", x.grad), ("grad_pos", pos.grad)] + [("grad." + k, p.grad) for k, p in enc.named_parameters()]
+    assert len(checks) == 2 + 11 * int(z["cfg"][3])
+    for k, g in checks:
+        ref = z[k]
+        scale = np.abs(ref).max() + 1e-4 * gmax
+        assert np.abs(g.cpu().numpy() - ref).max() <= 2e-3 * scale + 2e-6, k
+
+
+def _lib_launches():
+    from unipre3d_b200 import _lib
+    return _lib.launch_count
+
+
+def _clone_params(shapes, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return [torch.randn(s, generator=g).to(DEV).requires_grad_(True) for s in shapes]
+
+
+@pytest.mark.parametrize("gscale", [0.01, 30.0])      # below / above the clip threshold
+def test_fused_clip_adamw_matches_torch(gscale):
+    from unipre3d_b200.optim import FusedClipAdamW
+    shapes = [(384, 384), (1536,), (7, 3), (4099,), (1,), (128, 257)]
+    pa, pb = _clone_params(shapes, 0), _clone_params(shapes, 0)
+    shadows = {id(p): torch.zeros(p.shape, dtype=torch.bfloat16, device=DEV) for p in pa[:2]}
+    oa = FusedClipAdamW([{"params": pa[:3], "lr": 1e-3}, {"params": pa[3:], "lr": 3e-3}], lr=0.0, eps=1e-15,
+                        betas=(0.9, 0.999), max_norm=1.0, shadows=shadows)
+    ob = torch.optim.AdamW([{"params": pb[:3], "lr": 1e-3}, {"params": pb[3:], "lr": 3e-3}], lr=0.0, eps=1e-15,
+                           betas=(0.9, 0.999))
+    for step in range(5):
+        gg = torch.Generator(device="cpu").manual_seed(100 + step)
+        grads = [torch.randn(s, generator=gg).to(DEV) * gscale for s in shapes]
+        for p, q, g in zip(pa, pb, grads):
+            p.grad, q.grad = g.clone(), g.clone()
+        total = torch.nn.utils.clip_grad_norm_(pb, max_norm=1.0)
+        ob.step()
+        oa.step()
+        assert abs(oa.last_total_norm() - float(total)) <= 1e-5 * float(total)
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, atol=1e-6, rtol=1e-5), step
+        if step == 2:                       # StepLR-style in-place LR change on the device scalars
+            for g_ in oa.param_groups:
+                g_["lr"].mul_(0.5)
+            for g_ in ob.param_groups:
+                g_["lr"] *= 0.5
+    for p in pa[:2]:
+        assert torch.equal(shadows[id(p)], p.detach().to(torch.bfloat16))
+    assert oa.step_count() == 5
+    sd = oa.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 5.0
+    for p, q in zip(pa, pb):
+        assert torch.allclose(oa.state[p]["exp_avg"], ob.state[q]["exp_avg"], atol=1e-6, rtol=1e-5)
+        assert torch.allclose(oa.state[p]["exp_avg_sq"], ob.state[q]["exp_avg_sq"], atol=1e-7, rtol=1e-5)
+
+
+def test_fused_clip_adamw_skips_non_finite_step():
+    """train_network.py:336-340,368-384: a NaN/Inf gradient anywhere -> the whole step is skipped."""
+    from unipre3d_b200.optim import FusedClipAdamW
+    shapes = [(64, 64), (100,)]
+    ps = _clone_params(shapes, 1)
+    opt = FusedClipAdamW(ps, lr=1e-2, eps=1e-15, max_norm=1.0)
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    opt.step()
+    before = [p.detach().clone() for p in ps]
+    m_before = [opt.state[p]["exp_avg"].clone() for p in ps]
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    ps[1].grad[17] = float("nan")
+    opt.step()
+    assert opt.last_found_inf() and opt.step_count() == 1
+    for p, b, m in zip(ps, before, m_before):
+        assert torch.equal(p.detach(), b) and torch.equal(opt.state[p]["exp_avg"], m)
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    opt.step()
+    assert (not opt.last_found_inf()) and opt.step_count() == 2
+    assert not torch.equal(ps[0].detach(), before[0])

@@ -1,0 +1,259 @@
+"""The 16-Block transformer of the point backbone as ONE autograd node on B200.
+
+Arithmetic = /root/reference/openpoints/models/backbone/transformer.py:89-121 (Block: x + drop_path(attn(norm1(x))),
+x + drop_path(mlp(norm2(x)))) inside TransformerEncoder.forward's `x = block(x + pos)` loop (176-207), Attention
+(36-77) and Mlp (10-33).  The eager module graph spends ~60 launches per Block and step on 1.5 MB tensors; here each
+Block is 8 launches forward and ~17 backward:
+
+    forward   ln_fwd (residual + DropPath scale + pos + LayerNorm, one pass) -> qkv GEMM -> SDPA -> proj GEMM(+bias)
+              -> ln_fwd -> fc1 GEMM(+bias) -> gelu_fwd -> fc2 GEMM(+bias)
+    backward  2 GEMMs per Linear (dX in the activation dtype, dW written in fp32 by the GEMM), gelu_bwd (+ fc1 bias
+              gradient), ln_bwd (+ residual add, LayerNorm parameter gradients, dpos accumulation, DropPath scale,
+              cast and the bias gradient of the Linear in front -- all in the same pass), SDPA backward.
+
+The hand-written passes are libunipre3d_b200's up3d_ln_fwd / up3d_ln_bwd / up3d_gelu_* / up3d_scale_cast_colsum
+(csrc/backbone.cu); the dense GEMMs and the fused attention are library calls (cuBLASLt / cuDNN).  The residual
+stream, LayerNorm statistics and all parameter gradients are fp32; GEMM operands are fp32 (reference precision) or
+bf16 (tensor cores, persistent bf16 weight shadows from mixed_precision.ShadowWeights).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream_ptr
+
+_KEEP_CACHE = {}
+PARAMS_PER_BLOCK = 11   # norm1.w, norm1.b, qkv.w, proj.w, proj.b, norm2.w, norm2.b, fc1.w, fc1.b, fc2.w, fc2.b
+
+
+def _flag(dtype) -> int:
+    return 1 if dtype == torch.bfloat16 else 0
+
+
+def ln_fwd(x, delta, scale, pos, gamma, beta, eps, L, act_dtype, want_xs=True, want_y=True):
+    """xs = x + scale[b]*delta + pos ; y = LN(xs).  x (T,C) fp32 -> (xs fp32 | None, y act | None, mean, rstd)."""
+    T, C = x.shape
+    xs = torch.empty_like(x) if want_xs else None
+    y = torch.empty((T, C), dtype=act_dtype, device=x.device) if want_y else None
+    mean = torch.empty(T, dtype=torch.float32, device=x.device) if want_y else None
+    rstd = torch.empty(T, dtype=torch.float32, device=x.device) if want_y else None
+    check(_lib.lib.up3d_ln_fwd(_flag(act_dtype), T, L, C, ptr(x), ptr(delta), ptr(scale), ptr(pos), ptr(gamma), ptr(beta),
+                               float(eps), ptr(xs), ptr(y), ptr(mean), ptr(rstd), stream_ptr()), launches=1)
+    return xs, y, mean, rstd
+
+
+def ln_bwd(dy, xs, mean, rstd, gamma, g_res, scale, L, dpos, want_scaled, dgamma, dbeta, dbias):
+    T, C = xs.shape
+    dx = torch.empty_like(xs)
+    dscaled = torch.empty((T, C), dtype=dy.dtype, device=xs.device) if want_scaled else None
+    check(_lib.lib.up3d_ln_bwd(_flag(dy.dtype), T, L, C, ptr(dy), ptr(xs), ptr(mean), ptr(rstd), ptr(gamma), ptr(g_res),
+                               ptr(scale), ptr(dx), ptr(dpos), ptr(dscaled), ptr(dgamma), ptr(dbeta),
+                               ptr(dbias if want_scaled else None), stream_ptr()), launches=1)
+    return dx, dscaled
+
+
+def gelu_fwd(x):
+    y = torch.empty_like(x)
+    check(_lib.lib.up3d_gelu_fwd(_flag(x.dtype), x.numel(), ptr(x), ptr(y), stream_ptr()), launches=1)
+    return y
+
+
+def gelu_bwd(dy, pre, dbias):
+    T, C = pre.shape
+    dx = torch.empty_like(pre)
+    check(_lib.lib.up3d_gelu_bwd(_flag(pre.dtype), T, C, ptr(dy), ptr(pre), ptr(dx), ptr(dbias), stream_ptr()), launches=1)
+    return dx
+
+
+def scale_cast_colsum(g, scale, L, act_dtype, dbias):
+    T, C = g.shape
+    out = torch.empty((T, C), dtype=act_dtype, device=g.device)
+    check(_lib.lib.up3d_scale_cast_colsum(_flag(act_dtype), T, L, C, ptr(g), ptr(scale), ptr(out), ptr(dbias),
+                                          stream_ptr()), launches=1)
+    return out
+
+
+def _wgrad(dy, x):
+    """dW = dy^T @ x written in fp32 by the GEMM itself (no cast pass for the fp32 master gradient)."""
+    if dy.dtype == torch.float32:
+        return dy.t() @ x
+    return torch.mm(dy.t(), x, out_dtype=torch.float32)
+
+
+class _Meta:
+    """Non-tensor arguments of the stack (one object so that autograd sees a single opaque input)."""
+
+    def __init__(self, B, L, C, heads, scale, eps1, eps2, act_dtype, compute_weights):
+        self.B, self.L, self.C, self.heads, self.scale = B, L, C, heads, scale
+        self.eps1, self.eps2, self.act_dtype = eps1, eps2, act_dtype
+        self.compute_weights = compute_weights     # per block: (wqkv, wproj, bproj, w1, b1, w2, b2) in act dtype
+
+
+class EncoderStackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pos, masks, meta: _Meta, *params):
+        B, L, C, H = meta.B, meta.L, meta.C, meta.heads
+        T, D, act = B * L, C // H, meta.act_dtype
+        depth = len(params) // PARAMS_PER_BLOCK
+        require_cuda(x, pos)
+        xcur = x.reshape(T, C).contiguous().float()
+        pos2 = pos.reshape(T, C).contiguous().float()
+        pend, pend_scale = None, None
+        saved, attn_nodes = [], []
+        with torch.cuda.device(x.device), torch.autocast("cuda", enabled=False):
+            for i in range(depth):
+                n1w, n1b, _, _, _, n2w, n2b, _, _, _, _ = params[i * PARAMS_PER_BLOCK:(i + 1) * PARAMS_PER_BLOCK]
+                wqkv, wproj, bproj, w1, b1, w2, b2 = meta.compute_weights[i]
+                s1 = masks[2 * i] if masks is not None else None
+                s2 = masks[2 * i + 1] if masks is not None else None
+                xs, y1, mu1, rs1 = ln_fwd(xcur, pend, pend_scale, pos2, n1w, n1b, meta.eps1[i], L, act)
+                qkv = y1 @ wqkv.t()
+                with torch.enable_grad():
+                    qkv_l = qkv.detach().requires_grad_(True)
+                    q, k, v = qkv_l.view(B, L, 3, H, D).permute(2, 0, 3, 1, 4).unbind(0)
+                    o4 = F.scaled_dot_product_attention(q, k, v, scale=meta.scale)
+                    o_l = o4.transpose(1, 2).reshape(T, C)
+                o = o_l.detach()
+                a = F.linear(o, wproj, bproj)
+                x2, y2, mu2, rs2 = ln_fwd(xs, a, s1, None, n2w, n2b, meta.eps2[i], L, act)
+                pre = F.linear(y2, w1, b1)
+                h = gelu_fwd(pre)
+                d = F.linear(h, w2, b2)
+                saved += [xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h]
+                attn_nodes.append((qkv_l, o_l))
+                xcur, pend, pend_scale = x2, d, s2
+            out, _, _, _ = ln_fwd(xcur, pend, pend_scale, None, None, None, 0.0, L, act, want_y=False)
+        ctx.meta, ctx.depth, ctx.attn_nodes = meta, depth, attn_nodes
+        ctx.has_masks = masks is not None
+        ctx.save_for_backward(*(saved + list(params) + ([masks] if masks is not None else [])))
+        return out.view(B, L, C)
+
+    @staticmethod
+    def backward(ctx, gout):
+        meta, depth = ctx.meta, ctx.depth
+        B, L, C = meta.B, meta.L, meta.C
+        T, act = B * L, meta.act_dtype
+        sv = ctx.saved_tensors
+        n_act = 11 * depth
+        params = sv[n_act:n_act + PARAMS_PER_BLOCK * depth]
+        masks = sv[-1] if ctx.has_masks else None
+        Hd = meta.compute_weights[0][3].shape[0]
+        dev = gout.device
+        with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
+            g = gout.reshape(T, C).contiguous().float()
+            # all column-sum gradients of the stack in one zero-filled buffer (the kernels accumulate atomically)
+            per = 6 * C + Hd      # n1w n1b bproj n2w n2b b2 (C each) + b1 (Hd)
+            small = torch.zeros(depth * per, dtype=torch.float32, device=dev)
+            dpos = torch.zeros((T, C), dtype=torch.float32, device=dev)
+            grads: List[Optional[torch.Tensor]] = [None] * (PARAMS_PER_BLOCK * depth)
+
+            def sm(i, k, n=C):
+                o = i * per + k * C
+                return small[o:o + n]
+
+            # slots: 0 n1w, 1 n1b, 2 bproj, 3 n2w, 4 n2b, 5 b2, 6.. b1
+            s2_last = masks[2 * depth - 1] if masks is not None else None
+            dd = scale_cast_colsum(g, s2_last, L, act, sm(depth - 1, 5))
+            for i in range(depth - 1, -1, -1):
+                xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h = sv[11 * i:11 * i + 11]
+                n1w, _, _, _, _, n2w, _, _, _, _, _ = params[i * PARAMS_PER_BLOCK:(i + 1) * PARAMS_PER_BLOCK]
+                wqkv, wproj, _, w1, _, w2, _ = meta.compute_weights[i]
+                s1 = masks[2 * i] if masks is not None else None
+                s2_prev = masks[2 * i - 1] if (masks is not None and i > 0) else None
+                # ---- MLP branch
+                dh = dd @ w2
+                gw2 = _wgrad(dd, h)
+                dpre = gelu_bwd(dh, pre, sm(i, 6, Hd))
+                dy2 = dpre @ w1
+                gw1 = _wgrad(dpre, y2)
+                dx2, da = ln_bwd(dy2, x2, mu2, rs2, n2w, g, s1, L, None, True, sm(i, 3), sm(i, 4), sm(i, 2))
+                # ---- attention branch
+                do = da @ wproj
+                gwproj = _wgrad(da, o)
+                qkv_l, o_l = ctx.attn_nodes[i]
+                (dqkv,) = torch.autograd.grad(o_l, qkv_l, do)
+                dqkv = dqkv.contiguous()
+                dy1 = dqkv @ wqkv
+                gwqkv = _wgrad(dqkv, y1)
+                g, dd = ln_bwd(dy1, xs, mu1, rs1, n1w, dx2, s2_prev, L, dpos, i > 0, sm(i, 0), sm(i, 1),
+                               sm(i - 1, 5) if i > 0 else None)
+                base = i * PARAMS_PER_BLOCK
+                grads[base + 0], grads[base + 1] = sm(i, 0), sm(i, 1)
+                grads[base + 2], grads[base + 3], grads[base + 4] = gwqkv, gwproj, sm(i, 2)
+                grads[base + 5], grads[base + 6] = sm(i, 3), sm(i, 4)
+                grads[base + 7], grads[base + 8] = gw1, sm(i, 6, Hd)
+                grads[base + 9], grads[base + 10] = gw2, sm(i, 5)
+            ctx.attn_nodes = None
+        gx = g.view(B, L, C) if ctx.needs_input_grad[0] else None
+        gp = dpos.view(B, L, C) if ctx.needs_input_grad[1] else None
+        return (gx, gp, None, None) + tuple(grads)
+
+
+def supports(blocks) -> bool:
+    """The fused stack covers the configuration the reference instantiates (qkv_bias=False, no dropout, erf-GELU,
+    LayerNorm with affine parameters, width a multiple of 128)."""
+    import torch.nn as nn
+    for b in blocks:
+        C = b.norm1.normalized_shape[0]
+        if C % 128 != 0 or C // 128 not in (1, 2, 3, 4, 6, 8):
+            return False
+        if b.attn.qkv.bias is not None or b.attn.proj.bias is None or b.mlp.fc1.bias is None or b.mlp.fc2.bias is None:
+            return False
+        if b.attn.attn_drop.p != 0.0 or b.attn.proj_drop.p != 0.0 or b.mlp.drop.p != 0.0:
+            return False
+        if not isinstance(b.mlp.act, nn.GELU) or getattr(b.mlp.act, "approximate", "none") != "none":
+            return False
+        if not (isinstance(b.norm1, nn.LayerNorm) and b.norm1.elementwise_affine and b.norm1.bias is not None):
+            return False
+    return True
+
+
+def _compute_copy(lin, act_dtype):
+    """(weight, bias) of an nn.Linear in the GEMM operand dtype: the persistent bf16 shadows when they exist."""
+    if act_dtype == torch.float32:
+        return lin.weight.detach(), (None if lin.bias is None else lin.bias.detach())
+    w16 = getattr(lin, "_w16", None)
+    if w16 is None:
+        w16 = lin.weight.detach().to(act_dtype)
+        b16 = None if lin.bias is None else lin.bias.detach().to(act_dtype)
+    else:
+        b16 = lin._b16
+    return w16, b16
+
+
+def run_encoder_stack(blocks, x, pos, training: bool):
+    """blocks: nn.ModuleList of backbone.Block; x, pos (B,L,C) on CUDA -> (B,L,C) fp32."""
+    B, L, C = x.shape
+    act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+    if act not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"fused encoder stack: unsupported autocast dtype {act}")
+    params, cw, eps1, eps2, keep = [], [], [], [], []
+    for b in blocks:
+        params += [b.norm1.weight, b.norm1.bias, b.attn.qkv.weight, b.attn.proj.weight, b.attn.proj.bias,
+                   b.norm2.weight, b.norm2.bias, b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias]
+        wqkv, _ = _compute_copy(b.attn.qkv, act)
+        wproj, bproj = _compute_copy(b.attn.proj, act)
+        w1, b1 = _compute_copy(b.mlp.fc1, act)
+        w2, b2 = _compute_copy(b.mlp.fc2, act)
+        cw.append((wqkv, wproj, bproj, w1, b1, w2, b2))
+        eps1.append(b.norm1.eps)
+        eps2.append(b.norm2.eps)
+        p = float(getattr(b.drop_path, "drop_prob", 0.0))
+        keep += [1.0 - p, 1.0 - p]
+    masks = None
+    if training and any(k < 1.0 for k in keep):
+        # DropPath (timm semantics, scale_by_keep): one Bernoulli(keep)/keep factor per (branch, sample), all 2*depth
+        # branches drawn at once.  The keep-probability column is cached on the device (no H2D copy per step).
+        key = (x.device, tuple(keep))
+        kt = _KEEP_CACHE.get(key)
+        if kt is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("fused encoder stack: run one eager step before CUDA-graph capture")
+            kt = _KEEP_CACHE[key] = torch.tensor(keep, dtype=torch.float32, device=x.device).unsqueeze(1)
+        masks = (torch.rand(len(keep), B, device=x.device) < kt).float() / kt
+    meta = _Meta(B, L, C, blocks[0].attn.num_heads, float(blocks[0].attn.scale), eps1, eps2, act, cw)
+    return EncoderStackFn.apply(x, pos, masks, meta, *params)

@@ -107,11 +107,10 @@ class ModelManager:
         if cfg.opt.use_fusion:
             groups += [{"params": list(self.model.fusion_mlps.parameters()), "lr": base_lr},
                        {"params": list(self.model.image_conv.parameters()), "lr": base_lr}]
-        if capturable:  # tensor learning rates so a captured graph sees StepLR updates
-            for g in groups:
-                g["lr"] = torch.tensor(float(g["lr"]), device=device)
-        self.optimizer = torch.optim.AdamW(groups, lr=0.0 if not capturable else torch.tensor(0.0, device=device),
-                                           eps=1e-15, betas=tuple(cfg.opt.betas), fused=True, capturable=capturable)
+        # train_network.py:156-159 AdamW(lr=0.0, eps=1e-15, betas) + 368-390 clip_grad_norm_(1.0)/skip-on-NaN, fused
+        # (learning rates become device scalars at the first step, so a captured graph sees StepLR updates)
+        from .optim import FusedClipAdamW
+        self.optimizer = FusedClipAdamW(groups, lr=0.0, eps=1e-15, betas=tuple(cfg.opt.betas), max_norm=1.0)
         self.step_lr, self.lr_gamma, self._sched_step = cfg.opt.step_lr, cfg.opt.lr_gamma, 0
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if self.world > 1:
@@ -140,7 +139,8 @@ class ModelManager:
         if self._sched_step % self.step_lr == 0:
             for g in self.optimizer.param_groups:
                 if torch.is_tensor(g["lr"]):
-                    g["lr"].mul_(self.lr_gamma)
+                    with torch.no_grad():
+                        g["lr"].mul_(self.lr_gamma)
                 else:
                     g["lr"] = g["lr"] * self.lr_gamma
 
@@ -194,9 +194,9 @@ class Trainer:
         if autocast_dtype == torch.bfloat16 and shadow_weights:
             from .mixed_precision import ShadowWeights
             self._shadow = ShadowWeights(self.model_manager.model)
-        self.found_inf = torch.zeros((), dtype=torch.float32, device=self.device)
-        self.model_manager.optimizer.grad_scale = None
-        self.model_manager.optimizer.found_inf = self.found_inf
+            # the optimizer kernel rewrites the bf16 shadows together with the fp32 masters (no separate cast pass)
+            self.model_manager.optimizer.set_shadows(
+                {id(m): s for m, s in zip(self._shadow.masters, self._shadow.shadows)})
         self._flat_grad = None
         self._flat_views = None
         self.iteration = 0
@@ -258,19 +258,11 @@ class Trainer:
             p.grad = v
 
     def _clip_and_step(self) -> None:
-        """368-390 + 343-344: total norm on the device; non-finite -> found_inf=1 -> fused AdamW leaves
-        parameters and moments untouched; else grads are scaled to max_norm 1.0."""
+        """368-390 + 343-344 in three launches (optim.FusedClipAdamW): total norm on the device; non-finite -> the
+        update kernel leaves parameters, moments and the step counter untouched (the reference's `continue`); else
+        gradients are scaled to max_norm 1.0 inside the AdamW pass, which also rewrites the bf16 weight shadows."""
         mm = self.model_manager
-        grads = [p.grad for p in self.params if p.grad is not None]
-        norms = torch._foreach_norm(grads, 2.0)
-        total = torch.linalg.vector_norm(torch.stack(norms), 2.0)
-        self.found_inf.copy_((~torch.isfinite(total)).float())
-        coef = torch.clamp(1.0 / (total + 1e-6), max=1.0)
-        coef = torch.where(torch.isfinite(coef), coef, torch.zeros_like(coef))
-        torch._foreach_mul_(grads, coef)
         mm.optimizer.step()
-        if self._shadow is not None:
-            self._shadow.refresh()            # one multi-tensor fp32 -> bf16 copy for all Linear layers
         mm.optimizer.zero_grad(set_to_none=True)   # grads are re-materialised at the same graph-pool addresses on replay
 
     def _step_body(self, data) -> torch.Tensor:
