@@ -219,22 +219,42 @@ UP3D_API int up3d_scale_cast_colsum(int act_bf16, int T, int L, int C, const flo
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer step of train_network.py:333-352: `_check_and_clip_gradients` (368-390: skip the step when any
- * gradient is NaN/Inf, else clip_grad_norm_(max_norm=1.0)) + torch.optim.AdamW(eps=1e-15) (156-159) in three
+ * gradient is NaN/Inf, else clip_grad_norm_(max_norm=1.0)) + torch.optim.AdamW(eps=1e-15) (156-159) in two
  * launches over a multi-tensor work list: sum of squares -> (coef, found_inf) -> one read-modify-write pass
  * over param / exp_avg / exp_avg_sq (+ optional bf16 shadow of the new parameter values).
  *   work list: chunk c covers tensor chunk_tensor[c], elements [chunk_start[c], +up3d_adamw_chunk_elems());
  *   pointer tables (device arrays of device pointers, n_tensors each); bf16_shadows[i] may be NULL, and the
  *   table itself may be NULL; group[i] indexes lrs (device floats, so a captured CUDA graph sees LR changes).
- *   state: 8-byte aligned device buffer of 24 bytes, zero-initialised once:
- *          fp64 sum-of-squares accumulator | float step | float total_norm | float clip_coef | float found_inf.
+ *   state: 8-byte aligned device buffer of 32 bytes, zero-initialised once:
+ *          fp64 sum-of-squares accumulator | float step | float total_norm | float clip_coef | float found_inf |
+ *          uint32 ticket | pad.
  * A non-finite total norm leaves parameters, moments and the step counter untouched.
+ * up3d_adamw_step = up3d_grad_sumsq (1 launch) + up3d_adamw_apply (1 launch; its last CTA advances the step
+ * counter and clears the accumulator), exported separately so each pass can be timed on its own.
  * ---------------------------------------------------------------------------------------- */
 UP3D_API int up3d_adamw_chunk_elems(void);
+UP3D_API int up3d_grad_sumsq(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
+                             const int64_t *numel, const float *const *grads, void *state, up3d_stream_t stream);
+UP3D_API int up3d_adamw_apply(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
+                              const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
+                              float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
+                              float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
+                              up3d_stream_t stream);
 UP3D_API int up3d_adamw_step(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
                              const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
                              float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
                              float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
                              up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Frozen image stem (stand-in for model/image_predictor.py:56-81, whose SD-VAE weights are not shipped):
+ * the 128-channel field f[n,c,y,x] = sin(proj[c,:] . image[n,:,y,x] + shift[c]) feeds
+ * image_conv = GroupNorm(G, C) + Conv1x1 (model/gaussian_predictor.py:61-66,139).  Writes the GroupNorm
+ * statistics sums (n_images, G, 2) fp64 = [sum f, sum f^2] per (image, group) straight from the 3-channel
+ * image (n,3,H,W); the dense field is never materialised.  proj (C,3), shift (C); C <= 256, C % G == 0.
+ * ---------------------------------------------------------------------------------------- */
+UP3D_API int up3d_stem_group_stats(int n_images, int H, int W, int C, int G, const float *image, const float *proj,
+                                   const float *shift, double *sums, up3d_stream_t stream);
 
 #ifdef __cplusplus
 }

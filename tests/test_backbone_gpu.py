@@ -283,3 +283,32 @@ def test_fused_clip_adamw_skips_non_finite_step():
     opt.step()
     assert (not opt.last_found_inf()) and opt.step_count() == 2
     assert not torch.equal(ps[0].detach(), before[0])
+
+
+def test_stem_field_group_stats_and_gather_match_dense():
+    """csrc/stem.cu: GroupNorm statistics of the analytic stem field from the 3-channel image == var_mean of the dense
+    (n,128,R,R) tensor; sampled image_conv values/gradients identical through either route."""
+    from unipre3d_b200.fusion import LazyImageFeatures
+    from unipre3d_b200.gaussian_predictor import StemFeatureField
+    torch.manual_seed(6)
+    n, R, Cc, G, N = 3, 56, 128, 32, 40            # 56*56 is not a multiple of the block size: ragged last CTA
+    img = torch.rand(n, 3, R, R, device=DEV)
+    proj, shift = torch.randn(Cc, 3, device=DEV) * 0.7, torch.randn(Cc, device=DEV) * 0.3
+    field = StemFeatureField(img, proj, shift)
+    dense = field.dense()
+    assert dense.shape == field.shape == (n, Cc, R, R)
+    mean, var = field.group_stats(G)
+    var_ref, mean_ref = torch.var_mean(dense.reshape(n, G, -1), dim=2, unbiased=False)
+    assert torch.allclose(mean, mean_ref, atol=2e-6) and torch.allclose(var, var_ref, atol=2e-6, rtol=1e-5)
+    bidx = torch.arange(n, device=DEV).unsqueeze(1).expand(n, N)
+    ix, iy = torch.randint(0, R, (n, N), device=DEV), torch.randint(0, R, (n, N), device=DEV)
+    assert torch.allclose(field.gather(bidx, ix, iy), dense[bidx, :, ix, iy], atol=2e-6)
+    conv = torch.nn.Sequential(torch.nn.GroupNorm(G, Cc, eps=1e-6), torch.nn.Conv2d(Cc, 96, 1)).to(DEV)
+    w = torch.randn(n, N, 96, device=DEV)
+    a = LazyImageFeatures(field, conv).sample(bidx, ix, iy)
+    b = LazyImageFeatures(dense, conv).sample(bidx, ix, iy)
+    assert torch.allclose(a, b, atol=2e-5, rtol=1e-5)
+    ga = torch.autograd.grad((a * w).sum(), list(conv.parameters()))
+    gb = torch.autograd.grad((b * w).sum(), list(conv.parameters()))
+    for u, v in zip(ga, gb):
+        assert torch.allclose(u, v, atol=1e-4 * float(v.abs().max()) + 1e-6, rtol=1e-4)

@@ -56,8 +56,11 @@ def _load() -> C.CDLL:
         "up3d_gelu_fwd": (i32, [i32, i64, vp, vp, vp]),
         "up3d_gelu_bwd": (i32, [i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_scale_cast_colsum": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+        "up3d_stem_group_stats": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_adamw_chunk_elems": (i32, []),
         "up3d_adamw_step": (i32, [i32, i32] + [vp] * 10 + [f32] * 5 + [vp, vp]),
+        "up3d_adamw_apply": (i32, [i32, i32] + [vp] * 10 + [f32] * 5 + [vp, vp]),
+        "up3d_grad_sumsq": (i32, [i32, i32] + [vp] * 6),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -72,7 +75,8 @@ EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_residen
             "up3d_subsample_group", "up3d_knn", "up3d_raster_state_bytes", "up3d_raster_scratch_bytes", "up3d_raster_forward",
             "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_focal_l2_loss",
             "up3d_raster_timing_enable", "up3d_raster_timing_read", "up3d_ln_fwd", "up3d_ln_bwd", "up3d_gelu_fwd",
-            "up3d_gelu_bwd", "up3d_scale_cast_colsum", "up3d_adamw_chunk_elems", "up3d_adamw_step"]
+            "up3d_gelu_bwd", "up3d_scale_cast_colsum", "up3d_adamw_chunk_elems", "up3d_adamw_step", "up3d_adamw_apply",
+            "up3d_grad_sumsq", "up3d_stem_group_stats"]
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0

@@ -284,7 +284,7 @@ grad_sumsq_kernel(int n_chunks, const int *__restrict__ chunk_tensor, const int 
     }
 }
 
-// state (device, 8 floats + the fp64 accumulator in front):  acc (double) | step, total_norm, clip_coef, found_inf
+// state (device, 32 bytes):  fp64 sum-of-squares accumulator | float step, total_norm, clip_coef, found_inf | u32 ticket | pad
 struct AdamHyper { float beta1, beta2, eps, weight_decay, max_norm; };
 
 __device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g, float lr, float wd, float b1, float b2,
@@ -301,22 +301,19 @@ adamw_kernel(int n_chunks, const int *__restrict__ chunk_tensor, const int *__re
              const long long *__restrict__ numel, float *const *__restrict__ params, const float *const *__restrict__ grads,
              float *const *__restrict__ exp_avg, float *const *__restrict__ exp_avg_sq,
              __nv_bfloat16 *const *__restrict__ shadows, const int *__restrict__ group, const float *__restrict__ lrs,
-             const double *__restrict__ acc, float *__restrict__ state, AdamHyper h) {
-    // every CTA derives the same scalars from the accumulator (no grid sync needed)
+             double *__restrict__ acc, float *__restrict__ state, AdamHyper h) {
+    // every CTA derives the same scalars from the accumulator and the step counter (no grid sync needed); the LAST
+    // CTA to finish -- by then every CTA has read them -- publishes the diagnostics, advances the step counter and
+    // clears the accumulator for the next step (ticket in state[4])
     const float total = (float)sqrt(acc[0]);
     const bool bad = !isfinite(total);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        state[1] = total;
-        state[3] = bad ? 1.f : 0.f;
-    }
-    if (bad) return;                                    // train_network.py:336-340: skip the step, state untouched
     float coef = h.max_norm > 0.f ? h.max_norm / (total + 1e-6f) : 1.f;   // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
     coef = fminf(coef, 1.f);
-    if (blockIdx.x == 0 && threadIdx.x == 0) state[2] = coef;
-    const float t = state[0] + 1.f;                     // state[0] is advanced by adamw_finish_kernel AFTER this kernel
+    const float t = state[0] + 1.f;
     const float bc1 = 1.f - powf(h.beta1, t), bc2 = 1.f - powf(h.beta2, t);
     const float inv_bc2_sqrt = rsqrtf(bc2);
-    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    // bad: train_network.py:336-340 -- skip the step, parameters / moments / step counter untouched
+    for (int c = blockIdx.x; c < n_chunks && !bad; c += gridDim.x) {
         const int ti = chunk_tensor[c];
         const long long start = chunk_start[c], n = numel[ti];
         const long long end = min(n, start + (long long)ADAM_CHUNK);
@@ -359,11 +356,20 @@ adamw_kernel(int n_chunks, const int *__restrict__ chunk_tensor, const int *__re
             }
         }
     }
-}
-
-__global__ void adamw_finish_kernel(double *acc, float *state) {
-    if (state[3] == 0.f) state[0] += 1.f;      // the step counter only advances on applied steps
-    acc[0] = 0.0;                              // ready for the next step's sum of squares
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned *ticket = reinterpret_cast<unsigned *>(state + 4);
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            state[1] = total;
+            state[2] = bad ? 0.f : coef;
+            state[3] = bad ? 1.f : 0.f;
+            if (!bad) state[0] = t;            // the step counter only advances on applied steps
+            acc[0] = 0.0;                      // ready for the next step's sum of squares
+            *ticket = 0u;
+            __threadfence();
+        }
+    }
 }
 
 template <typename AT>
@@ -501,28 +507,49 @@ extern "C" int up3d_scale_cast_colsum(int act_bf16, int T, int L, int C, const f
 
 extern "C" int up3d_adamw_chunk_elems(void) { return ADAM_CHUNK; }
 
+static int adamw_check(int n_tensors, int n_chunks, const void *a, const void *b, const void *c, const void *state) {
+    UP3D_CHECK_ARG(n_tensors >= 0 && n_chunks >= 0, "up3d_adamw: bad sizes");
+    UP3D_CHECK_ARG(n_tensors == 0 || n_chunks == 0 || (a && b && c && state), "up3d_adamw: NULL pointer");
+    UP3D_CHECK_ARG((((uintptr_t)state) & 7) == 0, "up3d_adamw: state must be 8-byte aligned");
+    return 0;
+}
+
+extern "C" int up3d_grad_sumsq(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
+                               const int64_t *numel, const float *const *grads, void *state, up3d_stream_t stream) {
+    if (int rc = adamw_check(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, state)) return rc;
+    if (n_tensors == 0 || n_chunks == 0) return 0;
+    UP3D_CHECK_ARG(grads != nullptr, "up3d_grad_sumsq: NULL pointer");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    const int grid = min(n_chunks, UP3D_NUM_SMS * 8);
+    grad_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_chunks, chunk_tensor, chunk_start, (const long long *)numel,
+                                                             grads, (double *)state);
+    UP3D_LAUNCH_OK("grad_sumsq_kernel");
+    return 0;
+}
+
+extern "C" int up3d_adamw_apply(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
+                                const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
+                                float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
+                                float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
+                                up3d_stream_t stream) {
+    if (int rc = adamw_check(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, state)) return rc;
+    if (n_tensors == 0 || n_chunks == 0) return 0;
+    UP3D_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && group && lrs, "up3d_adamw_apply: NULL pointer");
+    const int grid = min(n_chunks, UP3D_NUM_SMS * 8);
+    AdamHyper h{beta1, beta2, eps, weight_decay, max_norm};
+    adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_chunks, chunk_tensor, chunk_start, (const long long *)numel, params,
+                                                        grads, exp_avg, exp_avg_sq, (__nv_bfloat16 *const *)bf16_shadows,
+                                                        group, lrs, (double *)state, (float *)state + 2, h);
+    UP3D_LAUNCH_OK("adamw_kernel");
+    return 0;
+}
+
 extern "C" int up3d_adamw_step(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
                                const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
                                float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
                                float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
                                up3d_stream_t stream) {
-    UP3D_CHECK_ARG(n_tensors >= 0 && n_chunks >= 0, "up3d_adamw_step: bad sizes");
-    if (n_tensors == 0 || n_chunks == 0) return 0;
-    UP3D_CHECK_ARG(chunk_tensor && chunk_start && numel && params && grads && exp_avg && exp_avg_sq && group && lrs && state,
-                   "up3d_adamw_step: NULL pointer");
-    UP3D_CHECK_ARG((((uintptr_t)state) & 7) == 0, "up3d_adamw_step: state must be 8-byte aligned");
-    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
-    cudaStream_t st = (cudaStream_t)stream;
-    double *acc = (double *)state;
-    float *fs = (float *)state + 2;
-    const int grid = min(n_chunks, UP3D_NUM_SMS * 8);
-    grad_sumsq_kernel<<<grid, 256, 0, st>>>(n_chunks, chunk_tensor, chunk_start, (const long long *)numel, grads, acc);
-    UP3D_LAUNCH_OK("grad_sumsq_kernel");
-    AdamHyper h{beta1, beta2, eps, weight_decay, max_norm};
-    adamw_kernel<<<grid, 256, 0, st>>>(n_chunks, chunk_tensor, chunk_start, (const long long *)numel, params, grads, exp_avg,
-                                       exp_avg_sq, (__nv_bfloat16 *const *)bf16_shadows, group, lrs, acc, fs, h);
-    UP3D_LAUNCH_OK("adamw_kernel");
-    adamw_finish_kernel<<<1, 1, 0, st>>>(acc, fs);
-    UP3D_LAUNCH_OK("adamw_finish_kernel");
-    return 0;
+    if (int rc = up3d_grad_sumsq(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, grads, state, stream)) return rc;
+    return up3d_adamw_apply(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, params, grads, exp_avg, exp_avg_sq,
+                            bf16_shadows, group, lrs, beta1, beta2, eps, weight_decay, max_norm, state, stream);
 }

@@ -23,13 +23,14 @@ class LazyImageFeatures:
     gradients while skipping ~0.8 GB/step of dense activations (and their backward) at 256x256.
     """
 
-    def __init__(self, decoder_features: torch.Tensor, image_conv: nn.Sequential):
-        self.x = decoder_features                      # (n, C_in, H, W), frozen (no grad)
-        self.gn, self.conv = image_conv[0], image_conv[1]
+    def __init__(self, decoder_features, image_conv: nn.Sequential):
+        self.x = decoder_features                      # (n, C_in, H, W) frozen tensor, or an analytic field with
+        self.gn, self.conv = image_conv[0], image_conv[1]   # .shape / .dense() / .group_stats(G) / .gather(b, ix, iy)
         self.shape = (decoder_features.shape[0], self.conv.out_channels, *decoder_features.shape[2:])
 
     def dense(self) -> torch.Tensor:
-        return self.conv(self.gn(self.x))
+        x = self.x if torch.is_tensor(self.x) else self.x.dense()
+        return self.conv(self.gn(x))
 
     def sample(self, bidx, ix, iy) -> torch.Tensor:
         """-> (B, N, C_out) = dense()[bidx, :, ix, iy]"""
@@ -37,9 +38,13 @@ class LazyImageFeatures:
         n, Cin, H, W = x.shape
         G = gn.num_groups
         with torch.no_grad():
-            var, mean = torch.var_mean(x.reshape(n, G, -1).float(), dim=2, unbiased=False)      # (n,G)
+            if torch.is_tensor(x):
+                var, mean = torch.var_mean(x.reshape(n, G, -1).float(), dim=2, unbiased=False)      # (n,G)
+                xs = x[bidx, :, ix, iy].float()                                                      # (B,N,Cin)
+            else:
+                mean, var = x.group_stats(G)
+                xs = x.gather(bidx, ix, iy)
             rstd = torch.rsqrt(var + gn.eps)
-            xs = x[bidx, :, ix, iy].float()                                                      # (B,N,Cin)
             cpg = Cin // G
             xs = (xs.reshape(*xs.shape[:2], G, cpg) - mean[:, None, :, None]) * rstd[:, None, :, None]
             xs = xs.reshape(*xs.shape[:2], Cin)

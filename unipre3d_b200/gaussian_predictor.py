@@ -34,8 +34,49 @@ def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
     return nn.init.trunc_normal_(tensor, mean=mean, std=std, a=a, b=b)
 
 
+class StemFeatureField:
+    """The stem's output f[n,c,y,x] = sin(proj[c,:] . image[n,:,y,x] + shift[c]) held analytically: `dense()`
+    materialises the (n,128,R,R) tensor the reference's image network would return; the B200 step only needs GroupNorm
+    group statistics (one kernel over the 3-channel image, csrc/stem.cu) and the field at the sampled pixels."""
+
+    def __init__(self, image: torch.Tensor, proj: torch.Tensor, shift: torch.Tensor):
+        self.image, self.proj, self.shift = image.float().contiguous(), proj, shift
+        n, _, H, W = image.shape
+        self.shape = (n, proj.shape[0], H, W)
+
+    @torch.no_grad()
+    def dense(self) -> torch.Tensor:
+        with torch.autocast(self.image.device.type, enabled=False):       # the frozen stem is defined in fp32
+            f = torch.einsum("oc,nchw->nohw", self.proj, self.image) + self.shift.view(1, -1, 1, 1)
+            return torch.sin(f)
+
+    @torch.no_grad()
+    def group_stats(self, num_groups: int):
+        """-> (mean, biased var), each (n, G), over each group's channels x pixels (torch.var_mean(unbiased=False))."""
+        from . import _lib
+        from ._lib import check, ptr, require_cuda, stream_ptr
+        require_cuda(self.image, self.proj, self.shift)
+        n, Cc, H, W = self.shape
+        sums = torch.empty((n, num_groups, 2), dtype=torch.float64, device=self.image.device)
+        with torch.cuda.device(self.image.device):
+            check(_lib.lib.up3d_stem_group_stats(n, H, W, Cc, num_groups, ptr(self.image), ptr(self.proj.contiguous()),
+                                                 ptr(self.shift.contiguous()), ptr(sums), stream_ptr()), launches=1)
+        cnt = float((Cc // num_groups) * H * W)
+        mean = sums[..., 0] / cnt
+        var = (sums[..., 1] / cnt - mean * mean).clamp_min(0.0)
+        return mean.float(), var.float()
+
+    @torch.no_grad()
+    def gather(self, bidx, ix, iy) -> torch.Tensor:
+        """-> (B, N, C) = dense()[bidx, :, ix, iy]"""
+        with torch.autocast(self.image.device.type, enabled=False):
+            px = self.image[bidx, :, ix, iy]                                # (B,N,3)
+            return torch.sin(px @ self.proj.t() + self.shift)
+
+
 class FrozenImageStem(nn.Module):
-    """Stand-in for ImageFeaturePredictor: frozen, gradient-free, returns {"decoder_block_3": (n,128,R,R)}."""
+    """Stand-in for ImageFeaturePredictor: frozen, gradient-free, returns {"decoder_block_3": (n,128,R,R)} -- as a
+    dense tensor, or (`lazy=True`, CUDA) as the analytic StemFeatureField the sampled image_conv path consumes."""
 
     def __init__(self, cfg, out_channels):
         super().__init__()
@@ -46,9 +87,9 @@ class FrozenImageStem(nn.Module):
         self.register_buffer("shift", torch.randn(128, generator=g) * 0.3, persistent=False)
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
-        f = torch.einsum("oc,nchw->nohw", self.proj, x.float()) + self.shift.view(1, -1, 1, 1)
-        return {"decoder_block_3": torch.sin(f)}
+    def forward(self, x: torch.Tensor, lazy: bool = False) -> Dict[str, torch.Tensor]:
+        field = StemFeatureField(x, self.proj, self.shift)
+        return {"decoder_block_3": field if (lazy and x.is_cuda) else field.dense()}
 
 
 class PointFeaturePredictor(nn.Module):
@@ -156,10 +197,11 @@ class GaussianSplatPredictor(nn.Module):
     def _forward_fusion(self, point_cloud, image, source_cameras_view_to_world=None, unprojected_coords=None):
         B, N_views = image.shape[0], image.shape[1]
         image = image.reshape(B * N_views, *image.shape[2:])
-        image_output = self.image_network.forward(image)
         if getattr(self.cfg.model, "dense_image_features", False):
+            image_output = self.image_network.forward(image)
             image_features = self.image_conv.forward(image_output["decoder_block_3"])     # reference dataflow
         else:
+            image_output = self.image_network.forward(image, lazy=True)
             image_features = LazyImageFeatures(image_output["decoder_block_3"], self.image_conv)
         point_features, center = self.point_network.forward_feat_fusion(
             point_cloud, image_features, source_cameras_view_to_world, self.fusion_mlps, self.intrinsic)

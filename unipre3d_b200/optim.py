@@ -1,4 +1,4 @@
-"""Gradient clipping + AdamW of the reference trainer as three launches.
+"""Gradient clipping + AdamW of the reference trainer as two launches.
 
 /root/reference/train_network.py:156-159 builds `torch.optim.AdamW(groups, lr=0.0, eps=1e-15, betas=cfg.opt.betas)`;
 every iteration runs `_check_and_clip_gradients` (368-390: per-parameter NaN/Inf scans -> skip the step, else
@@ -59,8 +59,8 @@ class FusedClipAdamW(torch.optim.AdamW):
         if any(tuple(g["betas"]) != tuple(g0["betas"]) or g["eps"] != g0["eps"] or g["weight_decay"] != g0["weight_decay"]
                for g in self.param_groups):
             raise NotImplementedError("FusedClipAdamW: betas/eps/weight_decay must be shared by all groups")
-        # device scalars: [fp64 sum of squares | step, total_norm, clip_coef, found_inf]
-        self._state = torch.zeros(6, dtype=torch.float32, device=dev)
+        # device scalars: [fp64 sum of squares | step, total_norm, clip_coef, found_inf | u32 ticket | pad]
+        self._state = torch.zeros(8, dtype=torch.float32, device=dev)
         self._step_view = self._state[2]
         # learning rates live on the device (a captured graph must see StepLR updates): group["lr"] becomes a view
         lrs = torch.zeros(len(self.param_groups), dtype=torch.float32, device=dev)
@@ -159,7 +159,7 @@ class FusedClipAdamW(torch.optim.AdamW):
                                            ptr(self._v_ptrs), ptr(self._s_ptrs), ptr(self._group), ptr(self._lrs),
                                            float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"]),
                                            float(g0["weight_decay"]), self.max_norm, ptr(self._state), stream_ptr()),
-                  launches=3)
+                  launches=2)
         return None
 
     # device scalars of the most recent step (reading them is a D2H sync: diagnostics / tests only)

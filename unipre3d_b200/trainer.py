@@ -258,7 +258,7 @@ class Trainer:
             p.grad = v
 
     def _clip_and_step(self) -> None:
-        """368-390 + 343-344 in three launches (optim.FusedClipAdamW): total norm on the device; non-finite -> the
+        """368-390 + 343-344 in two launches (optim.FusedClipAdamW): total norm on the device; non-finite -> the
         update kernel leaves parameters, moments and the step counter untouched (the reference's `continue`); else
         gradients are scaled to max_norm 1.0 inside the AdamW pass, which also rewrites the bf16 weight shadows."""
         mm = self.model_manager
