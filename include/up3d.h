@@ -247,6 +247,59 @@ UP3D_API int up3d_adamw_step(int n_tensors, int n_chunks, const int32_t *chunk_t
                              up3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Mini-PointNet of the tokenizer (openpoints/models/backbone/transformer.py:210-243 `Encoder`): the memory-bound
+ * passes around its four dense GEMMs.  Rows are (group, k): r = g*K + k, g < Gt = B*G, R = Gt*K.
+ * act_bf16 selects the dtype of the (R,C) / (Gt,C) activations (0 float, 1 __nv_bfloat16); statistics, partial
+ * sums and parameter gradients are fp32.  BatchNorm statistics are written as per-CTA partial sums
+ * (n_partials, 2, C) and reduced in fp64 by up3d_bn_reduce_finalize (deterministic, no atomics).
+ * stats (4,C) = batch mean, rstd, a = gamma*rstd, d = beta - mean*a.
+ * ---------------------------------------------------------------------------------------- */
+
+/* first layer Conv1d(3,128) (transformer.py:215, 230): nb is the tokenizer's (B,3,G,K) neighbourhood tensor
+ * (GK = G*K), W1 (128,3), b1 (128).  stats: partial sums of z = W1 x + b1 over n_partials CTAs. */
+UP3D_API int up3d_pn_conv1_stats(int R, int GK, const float *nb, const float *W1, const float *b1, float *partials,
+                                 int n_partials, up3d_stream_t stream);
+/* y1 (R,128) = ReLU(BatchNorm(W1 x + b1)) in one pass from the 3-channel input (transformer.py:215-217). */
+UP3D_API int up3d_pn_conv1_bn_relu(int act_bf16, int R, int GK, const float *nb, const float *W1, const float *b1,
+                                   const float *stats, void *y1, up3d_stream_t stream);
+/* backward of the same three ops from dy1 (R,128).  pass 0: partials (n_partials,2,128) of sum dy, sum dy*xhat (dy masked
+ * by the ReLU); pass 1 (sums (2,128) = reduced pass-0 partials): gW1 (128,3) += dz x^T, gb1 (128) += dz (atomic
+ * accumulate; zero them first), dz = a (dy - mean(dy) - xhat mean(dy xhat)), means = sums / count (count = the number of
+ * rows the batch statistics were taken over: R, or R * world under SyncBatchNorm). */
+UP3D_API int up3d_pn_conv1_bwd(int act_bf16, int pass, int R, int GK, const float *nb, const float *W1, const float *b1,
+                               const float *stats, const void *dy1, const float *sums, double count, float *partials,
+                               int n_partials, float *gW1, float *gb1, up3d_stream_t stream);
+/* partials (n_partials,2,C) -> sums (2,C) (may be NULL) and, when stats != NULL, the BatchNorm forward scalars
+ * stats (4,C) for `count` samples plus nn.BatchNorm1d's running-statistics update (momentum, unbiased variance;
+ * running_* and num_batches_tracked may be NULL). */
+UP3D_API int up3d_bn_reduce_finalize(int n_partials, int C, const float *partials, float *sums, double count,
+                                     const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                                     float *running_var, int64_t *num_batches_tracked, float *stats, up3d_stream_t stream);
+/* BatchNorm over z = zl + gpart[g] + bias (zl (R,C): the local half of Conv1d(512,512) on [global || local]
+ * (transformer.py:236-238); gpart (Gt,C) fp32: the global half, one row per group; both optional):
+ *   stats      : partials (ceil(Gt/gpc), 2, C) of sum z, sum z^2
+ *   apply_relu : y (R,C) = ReLU(a z + d)
+ *   bwd_reduce : partials of sum dy, sum dy*xhat (dy masked by the ReLU)
+ *   bwd_apply  : dz (R,C) = a (dy - mean(dy) - xhat mean(dy xhat)) and dgroup (Gt,C) = sum_k dz (the gradient of gpart) */
+UP3D_API int up3d_gbn_stats(int act_bf16, int Gt, int K, int C, int gpc, const void *zl, const float *gpart, const float *bias,
+                            float *partials, up3d_stream_t stream);
+UP3D_API int up3d_gbn_apply_relu(int act_bf16, int Gt, int K, int C, int gpc, const void *zl, const float *gpart,
+                                 const float *bias, const float *stats, void *y, up3d_stream_t stream);
+UP3D_API int up3d_gbn_bwd_reduce(int act_bf16, int Gt, int K, int C, int gpc, const void *dy, const void *zl, const float *gpart,
+                                 const float *bias, const float *stats, float *partials, up3d_stream_t stream);
+UP3D_API int up3d_gbn_bwd_apply(int act_bf16, int Gt, int K, int C, int gpc, const void *dy, const void *zl, const float *gpart,
+                                const float *bias, const float *stats, const float *sums, double count, void *dz,
+                                void *dgroup, up3d_stream_t stream);
+/* per-group max-pool over the K rows (torch.max(dim), transformer.py:235,242): out (Gt,C), arg (Gt,C) int32 = first
+ * arg-max row; its backward scatter dx (R,C) = dpooled at the arg-max row, 0 elsewhere; and
+ * dx = dlocal + scatter(dpooled) with colsum (C, may be NULL) += column sums of dx (atomic accumulate). */
+UP3D_API int up3d_group_max(int act_bf16, int Gt, int K, int C, const void *x, void *out, int32_t *arg, up3d_stream_t stream);
+UP3D_API int up3d_group_max_scatter(int act_bf16, int Gt, int K, int C, const void *dpooled, const int32_t *arg, void *dx,
+                                    up3d_stream_t stream);
+UP3D_API int up3d_group_combine(int act_bf16, int Gt, int K, int C, int gpc, const void *dlocal, const void *dpooled,
+                                const int32_t *arg, void *dx, float *colsum, up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Frozen image stem (stand-in for model/image_predictor.py:56-81, whose SD-VAE weights are not shipped):
  * the 128-channel field f[n,c,y,x] = sin(proj[c,:] . image[n,:,y,x] + shift[c]) feeds
  * image_conv = GroupNorm(G, C) + Conv1x1 (model/gaussian_predictor.py:61-66,139).  Writes the GroupNorm

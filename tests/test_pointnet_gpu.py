@@ -1,0 +1,96 @@
+"""Fused mini-PointNet (csrc/pointnet.cu + fused_pointnet.py) against the module path of backbone.Encoder -- itself
+pinned against the reference's Encoder by tests/golden/transformer_encoder.npz -- on the same seeded inputs."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _encoder(C=384, seed=0):
+    from unipre3d_b200.backbone import Encoder
+    torch.manual_seed(seed)
+    enc = Encoder(C).to(DEV)
+    with torch.no_grad():
+        for m in enc.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+    return enc
+
+
+@pytest.mark.parametrize("B,G,K", [(2, 16, 8), (3, 37, 32), (8, 128, 32)])
+def test_fused_mini_pointnet_equals_module_path_fp32(B, G, K):
+    from unipre3d_b200 import _lib, fused_pointnet
+    enc_a = _encoder()
+    enc_b = copy.deepcopy(enc_a)
+    enc_b.force_module_path = True
+    assert fused_pointnet.supports(enc_a)
+    torch.manual_seed(1)
+    nb = torch.randn(B, 3, G, K, device=DEV) * 0.05
+    w = torch.randn(B, G, 384, device=DEV)
+    enc_a.train(); enc_b.train()
+    before = _lib.launch_count
+    ta = enc_a.forward_grouped(nb)
+    assert _lib.launch_count > before, "the fused CUDA path did not run"
+    tb = enc_b.forward_grouped(nb)
+    assert ta.shape == tb.shape == (B, G, 384)
+    assert torch.allclose(ta, tb, atol=2e-4, rtol=1e-4), float((ta - tb).abs().max())
+    (ta * w).sum().backward()
+    (tb * w).sum().backward()
+    gmax = max(float(p.grad.abs().max()) for p in enc_b.parameters())
+    for (k, pa), (_, pb) in zip(enc_a.named_parameters(), enc_b.named_parameters()):
+        if k in ("first_conv.0.bias", "second_conv.0.bias"):
+            # bias in front of a train-mode BatchNorm: mathematically zero; the module path holds rounding noise
+            assert float(pa.grad.abs().max()) == 0.0 and float(pb.grad.abs().max()) <= 1e-2 * gmax, k
+            continue
+        scale = float(pb.grad.abs().max()) + 1e-4 * gmax
+        err = float((pa.grad - pb.grad).abs().max())
+        assert err <= 3e-3 * scale, (k, err, scale)
+    # running statistics (momentum 0.1, unbiased variance) and the batch counter
+    for ma, mb in zip(enc_a.modules(), enc_b.modules()):
+        if isinstance(ma, torch.nn.BatchNorm1d):
+            assert torch.allclose(ma.running_mean, mb.running_mean, atol=1e-5, rtol=1e-4)
+            assert torch.allclose(ma.running_var, mb.running_var, atol=1e-6, rtol=1e-4)
+            assert int(ma.num_batches_tracked) == int(mb.num_batches_tracked) == 1
+
+
+def test_fused_mini_pointnet_bf16_and_eval_dispatch():
+    enc = _encoder()
+    torch.manual_seed(2)
+    nb = torch.randn(4, 3, 64, 32, device=DEV) * 0.05
+    enc.train()
+    ref = enc.forward_grouped(nb)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = enc.forward_grouped(nb)
+    assert out.dtype == torch.bfloat16
+    assert float((out.float() - ref).abs().max()) <= 0.06 * float(ref.abs().max())
+    (out.float() ** 2).mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.dtype == torch.float32 for p in enc.parameters())
+    # eval mode: the module path with running statistics
+    enc.eval()
+    a = enc.forward_grouped(nb)
+    b = enc.forward(nb.permute(0, 2, 3, 1))
+    assert torch.equal(a, b)
+
+
+def test_group_max_first_occurrence_and_scatter():
+    from unipre3d_b200 import _lib
+    from unipre3d_b200._lib import check, ptr, stream_ptr
+    Gt, K, C = 5, 32, 256
+    torch.manual_seed(3)
+    x = torch.randint(0, 4, (Gt * K, C), device=DEV).float()         # many ties
+    out = torch.empty(Gt, C, device=DEV)
+    arg = torch.empty(Gt, C, dtype=torch.int32, device=DEV)
+    check(_lib.lib.up3d_group_max(0, Gt, K, C, ptr(x), ptr(out), ptr(arg), stream_ptr()), 1)
+    x3 = x.view(Gt, K, C)
+    assert torch.equal(out, x3.max(1)[0])
+    first = (x3 == x3.max(1, keepdim=True)[0]).float().argmax(1)     # first maximal row
+    assert torch.equal(arg.long(), first)
+    d = torch.randn(Gt, C, device=DEV)
+    dx = torch.empty(Gt * K, C, device=DEV)
+    check(_lib.lib.up3d_group_max_scatter(0, Gt, K, C, ptr(d), ptr(arg), ptr(dx), stream_ptr()), 1)
+    ref = torch.zeros(Gt, K, C, device=DEV).scatter_(1, first.unsqueeze(1), d.unsqueeze(1))
+    assert torch.equal(dx.view(Gt, K, C), ref)

@@ -160,6 +160,17 @@ class Encoder(nn.Module):
         return fg.reshape(bs, g, self.encoder_channel)
 
 
+    def forward_grouped(self, neighborhood):
+        """neighborhood (B,3,G,K), the tokenizer's own layout -> (B,G,C).  On CUDA in train mode this is ONE autograd
+        node over the fused kernels of csrc/pointnet.cu (fused_pointnet.py); `forward` is the same arithmetic as
+        module calls (eval mode, CPU parity tests)."""
+        if neighborhood.is_cuda and self.training and not getattr(self, "force_module_path", False):
+            from . import fused_pointnet
+            if fused_pointnet.supports(self):
+                return fused_pointnet.run_mini_pointnet(self, neighborhood)
+        return self.forward(neighborhood.permute(0, 2, 3, 1))
+
+
 class SubsampleGroup(nn.Module):
     """group_embed.py:14-57 restricted to what the path uses: FPS subsample + ball-query grouping."""
 
@@ -202,7 +213,7 @@ class PointTransformerEncoder(nn.Module):
             pts = pts["pos"]
         pts = pts[:, :, :3].contiguous()
         neighborhood, center = self.group_divider(pts)                       # (B,3,G,K), (B,G,3)
-        group_input_tokens = self.encoder(neighborhood.permute(0, 2, 3, 1))  # (B,G,K,3) -> (B,G,C)
+        group_input_tokens = self.encoder.forward_grouped(neighborhood)      # (B,3,G,K) -> (B,G,C)
         group_input_tokens = self.reduce_dim(group_input_tokens)
         cls_tokens = self.cls_token.expand(group_input_tokens.size(0), -1, -1)
         cls_pos = self.cls_pos.expand(group_input_tokens.size(0), -1, -1)

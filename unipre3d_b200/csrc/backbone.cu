@@ -222,21 +222,36 @@ col_tile_kernel(int T, int L, int Ccols, int rows_per_cta, const void *__restric
     if (col >= Ccols) return;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(T, r0 + rows_per_cta);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int row = r0; row < r1; ++row) {
-        const size_t o = (size_t)row * Ccols + col;
-        float4 q;
-        if (MODE == 0) {
-            const float4 d = Vec4<AT>::load(reinterpret_cast<const AT *>(in0_) + o);
-            const float4 p = Vec4<AT>::load(pre + o);
-            q = make_float4(d.x * gelu_grad_f(p.x), d.y * gelu_grad_f(p.y), d.z * gelu_grad_f(p.z), d.w * gelu_grad_f(p.w));
-        } else {
-            const float4 g = Vec4<float>::load(reinterpret_cast<const float *>(in0_) + o);
-            const float s = scale ? scale[row / L] : 1.f;
-            q = make_float4(s * g.x, s * g.y, s * g.z, s * g.w);
+    constexpr int U = 4;                       // rows in flight per thread: all loads of a batch are issued first
+    for (int rb = r0; rb < r1; rb += U) {
+        float4 a[U], p[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int row = min(rb + u, r1 - 1);
+            const size_t o = (size_t)row * Ccols + col;
+            if (MODE == 0) {
+                a[u] = Vec4<AT>::load(reinterpret_cast<const AT *>(in0_) + o);
+                p[u] = Vec4<AT>::load(pre + o);
+            } else {
+                a[u] = Vec4<float>::load(reinterpret_cast<const float *>(in0_) + o);
+            }
         }
-        Vec4<AT>::store(out + o, q);
-        q = Vec4<AT>::round(q);
-        acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int row = rb + u;
+            if (row >= r1) break;
+            float4 q;
+            if (MODE == 0) {
+                q = make_float4(a[u].x * gelu_grad_f(p[u].x), a[u].y * gelu_grad_f(p[u].y), a[u].z * gelu_grad_f(p[u].z),
+                                a[u].w * gelu_grad_f(p[u].w));
+            } else {
+                const float s = scale ? scale[row / L] : 1.f;
+                q = make_float4(s * a[u].x, s * a[u].y, s * a[u].z, s * a[u].w);
+            }
+            Vec4<AT>::store(out + (size_t)row * Ccols + col, q);
+            q = Vec4<AT>::round(q);
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
     }
     if (dbias) {
         atomicAdd(dbias + col, acc.x); atomicAdd(dbias + col + 1, acc.y);
@@ -472,8 +487,8 @@ static int launch_col_tile(int act_bf16, int T, int L, int C, const void *in0, c
         if ((C / 4) % t == 0) { threads = t; break; }
     if (C / 4 < 32) threads = 32;
     const int gy = div_up(C / 4, threads);
-    // ~1 wave of CTAs: rows per CTA so that grid.x * grid.y ~ number of SMs
-    int rows = max(1, div_up(T * gy, UP3D_NUM_SMS));
+    // ~4 resident CTAs per SM (latency hiding), at least 4 rows per CTA so the column-sum atomics stay few
+    int rows = max(4, div_up(T * gy, UP3D_NUM_SMS * 4));
     const dim3 grid(div_up(T, rows), gy);
     if (act_bf16)
         col_tile_kernel<__nv_bfloat16, MODE><<<grid, threads, 0, st>>>(T, L, C, rows, in0, (const __nv_bfloat16 *)pre, scale,

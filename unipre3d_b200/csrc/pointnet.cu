@@ -1,0 +1,570 @@
+// pointnet.cu -- the per-group mini-PointNet of the tokenizer (openpoints/models/backbone/transformer.py:210-243
+// `Encoder`) around its four dense GEMMs:
+//
+//     x (B,G,K,3) -Conv1d(3,128)-> BN -> ReLU -Conv1d(128,256)-> f ; fg = max_K f ; [fg || f] -Conv1d(512,512)-> BN -> ReLU
+//       -Conv1d(512,C)-> max_K -> tokens (B,G,C)
+//
+// The dense 1x1 convolutions stay library GEMMs over R = B*G*K rows.  Everything else -- the K=3 first layer, both
+// train-mode BatchNorms (statistics, normalise+ReLU, and their backward reductions), the per-group max-pools and their
+// scatter backward, and the "global || local" concat (never materialised: W3 [fg || f] = W3g fg + W3l f, so the global
+// half is a (B*G)-row GEMM whose result is broadcast over the K rows inside the BatchNorm passes) -- are the fused
+// kernels below.  BatchNorm statistics are per-CTA partial sums reduced in fp64 by a finalize kernel (deterministic,
+// no atomics); the conv biases in front of a train-mode BatchNorm have a mathematically zero gradient.
+//
+// Rows are (group, k): r = g*K + k, g < Gt = B*G.  Activations between GEMMs are AT = float or __nv_bfloat16.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace up3d {
+
+template <typename AT> struct PVec4;
+template <> struct PVec4<float> {
+    static __device__ __forceinline__ float4 load(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+    static __device__ __forceinline__ void store(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+};
+template <> struct PVec4<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 load(const __nv_bfloat16 *p) {
+        const uint2 r = *reinterpret_cast<const uint2 *>(p);
+        const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+        const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, float4 v) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 r;
+        r.x = *reinterpret_cast<const unsigned *>(&a);
+        r.y = *reinterpret_cast<const unsigned *>(&b);
+        *reinterpret_cast<uint2 *>(p) = r;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ first layer (K = 3)
+// nb is the tokenizer's (B,3,G,K) neighbourhood tensor: row r = b*GK + j reads nb[(b*3 + k)*GK + j].
+constexpr int PN_TILE = 128;      // rows per CTA tile of the first-layer kernels
+constexpr int PN_C1 = 128;        // channels of the first layer (thread = channel)
+
+__device__ __forceinline__ void pn_load_x_tile(float (*xs)[PN_TILE], const float *__restrict__ nb, int R, int GK, int r0) {
+    for (int i = threadIdx.x; i < 3 * PN_TILE; i += blockDim.x) {
+        const int k = i / PN_TILE, rr = i - k * PN_TILE, r = r0 + rr;
+        float v = 0.f;
+        if (r < R) {
+            const int b = r / GK, j = r - b * GK;
+            v = nb[((size_t)b * 3 + k) * GK + j];
+        }
+        xs[k][rr] = v;
+    }
+}
+
+// partials (gridDim.x, 2, C1): per-CTA sum z, sum z^2 of z = W1 x + b1
+__global__ void __launch_bounds__(PN_C1)
+pn_conv1_stats_kernel(int R, int GK, const float *__restrict__ nb, const float *__restrict__ W1, const float *__restrict__ b1,
+                      float *__restrict__ partials) {
+    __shared__ float xs[3][PN_TILE];
+    const int c = threadIdx.x;
+    const float w0 = W1[3 * c], w1 = W1[3 * c + 1], w2 = W1[3 * c + 2], bb = b1[c];
+    float s = 0.f, q = 0.f;
+    for (int r0 = blockIdx.x * PN_TILE; r0 < R; r0 += gridDim.x * PN_TILE) {
+        __syncthreads();
+        pn_load_x_tile(xs, nb, R, GK, r0);
+        __syncthreads();
+        const int n = min(PN_TILE, R - r0);
+        for (int rr = 0; rr < n; ++rr) {
+            const float z = fmaf(w0, xs[0][rr], fmaf(w1, xs[1][rr], fmaf(w2, xs[2][rr], bb)));
+            s += z;
+            q = fmaf(z, z, q);
+        }
+    }
+    partials[((size_t)blockIdx.x * 2 + 0) * PN_C1 + c] = s;
+    partials[((size_t)blockIdx.x * 2 + 1) * PN_C1 + c] = q;
+}
+
+// y1[r, c] = relu(a[c] * (W1 x_r + b1)[c] + d[c]);  stats (4, C1): mean, rstd, a = gamma*rstd, d = beta - mean*a
+template <typename AT>
+__global__ void __launch_bounds__(256)
+pn_conv1_bn_relu_kernel(int R, int GK, const float *__restrict__ nb, const float *__restrict__ W1, const float *__restrict__ b1,
+                        const float *__restrict__ stats, AT *__restrict__ y1) {
+    __shared__ float xs[3][PN_TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = 4 * lane;
+    float w[4][3], bb[4], a[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        w[i][0] = W1[3 * (c0 + i)]; w[i][1] = W1[3 * (c0 + i) + 1]; w[i][2] = W1[3 * (c0 + i) + 2];
+        bb[i] = b1[c0 + i];
+        a[i] = stats[2 * PN_C1 + c0 + i];
+        d[i] = stats[3 * PN_C1 + c0 + i];
+    }
+    for (int r0 = blockIdx.x * PN_TILE; r0 < R; r0 += gridDim.x * PN_TILE) {
+        __syncthreads();
+        pn_load_x_tile(xs, nb, R, GK, r0);
+        __syncthreads();
+        const int n = min(PN_TILE, R - r0);
+        for (int rr = warp; rr < n; rr += 8) {
+            const float x0 = xs[0][rr], x1 = xs[1][rr], x2 = xs[2][rr];
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float z = fmaf(w[i][0], x0, fmaf(w[i][1], x1, fmaf(w[i][2], x2, bb[i])));
+                o[i] = fmaxf(fmaf(a[i], z, d[i]), 0.f);
+            }
+            PVec4<AT>::store(y1 + (size_t)(r0 + rr) * PN_C1 + c0, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+}
+
+// backward of ReLU + BatchNorm + first layer.  PASS 0: partials (gridDim.x, 2, C1) of sum dy, sum dy*xhat with
+// dy = dy1 * [a z + d > 0].  PASS 1: dz = a (dy - m1 - xhat m2) with m = sums / R; accumulates gW1 (C1,3) += dz x^T,
+// gb1 (C1) += dz (float atomics, one per CTA and entry).
+template <typename AT, int PASS>
+__global__ void __launch_bounds__(PN_C1)
+pn_conv1_bwd_kernel(int R, int GK, const float *__restrict__ nb, const float *__restrict__ W1, const float *__restrict__ b1,
+                    const float *__restrict__ stats, const AT *__restrict__ dy1, const float *__restrict__ sums,
+                    float inv_count, float *__restrict__ partials, float *__restrict__ gW1, float *__restrict__ gb1) {
+    __shared__ float xs[3][PN_TILE];
+    const int c = threadIdx.x;
+    const float w0 = W1[3 * c], w1 = W1[3 * c + 1], w2 = W1[3 * c + 2], bb = b1[c];
+    const float mean = stats[c], rstd = stats[PN_C1 + c], a = stats[2 * PN_C1 + c], d = stats[3 * PN_C1 + c];
+    float m1 = 0.f, m2 = 0.f;
+    if (PASS == 1) { m1 = sums[c] * inv_count; m2 = sums[PN_C1 + c] * inv_count; }
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    for (int r0 = blockIdx.x * PN_TILE; r0 < R; r0 += gridDim.x * PN_TILE) {
+        __syncthreads();
+        pn_load_x_tile(xs, nb, R, GK, r0);
+        __syncthreads();
+        const int n = min(PN_TILE, R - r0);
+#pragma unroll 8
+        for (int rr = 0; rr < n; ++rr) {
+            const float x0 = xs[0][rr], x1 = xs[1][rr], x2 = xs[2][rr];
+            const float z = fmaf(w0, x0, fmaf(w1, x1, fmaf(w2, x2, bb)));
+            const float g = (float)dy1[(size_t)(r0 + rr) * PN_C1 + c];
+            const float dy = fmaf(a, z, d) > 0.f ? g : 0.f;
+            const float xh = (z - mean) * rstd;
+            if (PASS == 0) {
+                acc0 += dy;
+                acc1 = fmaf(dy, xh, acc1);
+            } else {
+                const float dz = a * (dy - m1 - xh * m2);
+                acc0 = fmaf(dz, x0, acc0); acc1 = fmaf(dz, x1, acc1); acc2 = fmaf(dz, x2, acc2);
+                acc3 += dz;
+            }
+        }
+    }
+    if (PASS == 0) {
+        partials[((size_t)blockIdx.x * 2 + 0) * PN_C1 + c] = acc0;
+        partials[((size_t)blockIdx.x * 2 + 1) * PN_C1 + c] = acc1;
+    } else {
+        atomicAdd(gW1 + 3 * c, acc0); atomicAdd(gW1 + 3 * c + 1, acc1); atomicAdd(gW1 + 3 * c + 2, acc2);
+        atomicAdd(gb1 + c, acc3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ partial-sum reduction / BN finalize
+// partials (nPart, 2, C) -> sums (2, C) [fp64 accumulation]; when stats != NULL also the BatchNorm forward scalars
+// stats (4, C) = mean, rstd, a, d and the running-statistics update of nn.BatchNorm1d (momentum, unbiased variance).
+// grid = ceil(C / 32), block = (32, 8).
+__global__ void __launch_bounds__(256)
+bn_reduce_finalize_kernel(int nPart, int C, const float *__restrict__ partials, float *__restrict__ sums, double count,
+                          const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
+                          float *__restrict__ running_mean, float *__restrict__ running_var, long long *__restrict__ nbt,
+                          float *__restrict__ stats) {
+    __shared__ double sh[2][8][32];
+    const int c = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        for (int p = ly; p < nPart; p += 8) {
+            s += (double)partials[((size_t)p * 2 + 0) * C + c];
+            q += (double)partials[((size_t)p * 2 + 1) * C + c];
+        }
+    }
+    sh[0][ly][threadIdx.x] = s;
+    sh[1][ly][threadIdx.x] = q;
+    __syncthreads();
+    if (ly == 0 && c < C) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x]; q += sh[1][i][threadIdx.x]; }
+        if (sums) { sums[c] = (float)s; sums[C + c] = (float)q; }
+        if (stats) {
+            const double mean = s / count;
+            double var = q / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+            const float a = gamma[c] * rstd;
+            stats[c] = (float)mean;
+            stats[C + c] = rstd;
+            stats[2 * C + c] = a;
+            stats[3 * C + c] = beta[c] - (float)mean * a;
+            if (running_mean) {
+                const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+        }
+    }
+    if (nbt && blockIdx.x == 0 && threadIdx.x == 0 && ly == 0) nbt[0] += 1;
+}
+
+// ------------------------------------------------------------------------------------------ group-tile kernels over (R, C)
+// CTA = `gpc` consecutive groups x one column tile; blockDim = (CT column threads, RL row lanes); a column thread owns
+// 4 consecutive columns; row lane l handles rows k = l, l+RL, ... of each group.
+constexpr int GT_RL = 4;
+constexpr int GT_MAXK = 64;       // rows of a group handled per lane are unrolled in batches of 8
+
+struct GroupTileArgs {
+    int Gt, K, C, gpc;
+    float inv_count;              // 1 / R (backward)
+    const void *in0;              // MODE-dependent main (R, C) input, AT
+    const void *in1;              // second (R, C) input, AT
+    const float *gpart;           // (Gt, C) fp32 broadcast term (global half of the concat GEMM), may be NULL
+    const float *bias;            // (C) conv bias added to in0 + gpart, may be NULL
+    const float *stats;           // (4, C): mean, rstd, a, d
+    const float *sums;            // (2, C): backward sums
+    const int *arg;               // (Gt, C) arg-max row of each group
+    const void *small_in;         // (Gt, C) per-group input (max_scatter: d tokens; combine: dfg), AT
+    void *out;                    // (R, C) AT
+    void *small_out;              // (Gt, C): group_max values (AT) / bn_bwd_apply group sums (AT)
+    int *arg_out;                 // (Gt, C)
+    float *partials;              // (gridDim.x, 2, C)
+    float *colsum;                // (C) float atomics
+};
+
+enum { GT_STATS = 0, GT_APPLY = 1, GT_BWD_REDUCE = 2, GT_BWD_APPLY = 3, GT_MAX = 4, GT_SCATTER = 5, GT_COMBINE = 6 };
+
+template <typename AT, int MODE>
+__global__ void __launch_bounds__(512)
+group_tile_kernel(GroupTileArgs A) {
+    __shared__ float4 sh0[GT_RL][128];
+    __shared__ float4 sh1[GT_RL][128];
+    const int ct = threadIdx.x, lane_r = threadIdx.y;
+    const int col = (blockIdx.y * blockDim.x + ct) * 4;
+    const bool col_ok = col < A.C;
+    const int C = A.C, K = A.K;
+    const AT *in0 = reinterpret_cast<const AT *>(A.in0);
+    const AT *in1 = reinterpret_cast<const AT *>(A.in1);
+    AT *out = reinterpret_cast<AT *>(A.out);
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), mean = bias, rstd = bias, a = bias, d = bias, m1 = bias, m2 = bias;
+    if (col_ok) {
+        if (A.bias) bias = *reinterpret_cast<const float4 *>(A.bias + col);
+        if (A.stats) {
+            mean = *reinterpret_cast<const float4 *>(A.stats + col);
+            rstd = *reinterpret_cast<const float4 *>(A.stats + C + col);
+            a = *reinterpret_cast<const float4 *>(A.stats + 2 * C + col);
+            d = *reinterpret_cast<const float4 *>(A.stats + 3 * C + col);
+        }
+        if (MODE == GT_BWD_APPLY) {
+            m1 = *reinterpret_cast<const float4 *>(A.sums + col);
+            m2 = *reinterpret_cast<const float4 *>(A.sums + C + col);
+            m1.x *= A.inv_count; m1.y *= A.inv_count; m1.z *= A.inv_count; m1.w *= A.inv_count;
+            m2.x *= A.inv_count; m2.y *= A.inv_count; m2.z *= A.inv_count; m2.w *= A.inv_count;
+        }
+    }
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;       // per-CTA partial sums (STATS / BWD_REDUCE / COMBINE)
+    const int g_begin = blockIdx.x * A.gpc, g_end = min(A.Gt, g_begin + A.gpc);
+    for (int g = g_begin; g < g_end; ++g) {
+        float4 gp = bias;                                         // broadcast term of this group: gpart + bias
+        if (col_ok && A.gpart) {
+            const float4 t = *reinterpret_cast<const float4 *>(A.gpart + (size_t)g * C + col);
+            gp.x += t.x; gp.y += t.y; gp.z += t.z; gp.w += t.w;
+        }
+        float4 small = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 am = make_int4(-1, -1, -1, -1);
+        if (col_ok && (MODE == GT_SCATTER || MODE == GT_COMBINE)) {
+            small = PVec4<AT>::load(reinterpret_cast<const AT *>(A.small_in) + (size_t)g * C + col);
+            am = *reinterpret_cast<const int4 *>(A.arg + (size_t)g * C + col);
+        }
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        int4 bidx = make_int4(0, 0, 0, 0);
+        float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);             // group sum (BWD_APPLY)
+        for (int kb = lane_r; kb < K; kb += GT_RL * 8) {
+            float4 u[8], v[8];
+            if (MODE != GT_SCATTER) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = kb + i * GT_RL;
+                    if (k < K && col_ok) {
+                        const size_t o = ((size_t)g * K + k) * C + col;
+                        u[i] = PVec4<AT>::load(in0 + o);
+                        if (MODE == GT_BWD_REDUCE || MODE == GT_BWD_APPLY) v[i] = PVec4<AT>::load(in1 + o);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = kb + i * GT_RL;
+                if (k >= K || !col_ok) continue;
+                const size_t o = ((size_t)g * K + k) * C + col;
+                if (MODE == GT_STATS) {
+                    const float z0 = u[i].x + gp.x, z1 = u[i].y + gp.y, z2 = u[i].z + gp.z, z3 = u[i].w + gp.w;
+                    p0.x += z0; p0.y += z1; p0.z += z2; p0.w += z3;
+                    p1.x = fmaf(z0, z0, p1.x); p1.y = fmaf(z1, z1, p1.y); p1.z = fmaf(z2, z2, p1.z); p1.w = fmaf(z3, z3, p1.w);
+                } else if (MODE == GT_APPLY) {
+                    float4 y;
+                    y.x = fmaxf(fmaf(a.x, u[i].x + gp.x, d.x), 0.f);
+                    y.y = fmaxf(fmaf(a.y, u[i].y + gp.y, d.y), 0.f);
+                    y.z = fmaxf(fmaf(a.z, u[i].z + gp.z, d.z), 0.f);
+                    y.w = fmaxf(fmaf(a.w, u[i].w + gp.w, d.w), 0.f);
+                    PVec4<AT>::store(out + o, y);
+                } else if (MODE == GT_BWD_REDUCE || MODE == GT_BWD_APPLY) {
+                    // u = dy (gradient of the ReLU output), v = zl (pre-BN local GEMM output)
+                    const float z0 = v[i].x + gp.x, z1 = v[i].y + gp.y, z2 = v[i].z + gp.z, z3 = v[i].w + gp.w;
+                    const float g0 = fmaf(a.x, z0, d.x) > 0.f ? u[i].x : 0.f, g1 = fmaf(a.y, z1, d.y) > 0.f ? u[i].y : 0.f;
+                    const float g2 = fmaf(a.z, z2, d.z) > 0.f ? u[i].z : 0.f, g3 = fmaf(a.w, z3, d.w) > 0.f ? u[i].w : 0.f;
+                    const float h0 = (z0 - mean.x) * rstd.x, h1 = (z1 - mean.y) * rstd.y;
+                    const float h2 = (z2 - mean.z) * rstd.z, h3 = (z3 - mean.w) * rstd.w;
+                    if (MODE == GT_BWD_REDUCE) {
+                        p0.x += g0; p0.y += g1; p0.z += g2; p0.w += g3;
+                        p1.x = fmaf(g0, h0, p1.x); p1.y = fmaf(g1, h1, p1.y); p1.z = fmaf(g2, h2, p1.z); p1.w = fmaf(g3, h3, p1.w);
+                    } else {
+                        float4 dz;
+                        dz.x = a.x * (g0 - m1.x - h0 * m2.x); dz.y = a.y * (g1 - m1.y - h1 * m2.y);
+                        dz.z = a.z * (g2 - m1.z - h2 * m2.z); dz.w = a.w * (g3 - m1.w - h3 * m2.w);
+                        PVec4<AT>::store(out + o, dz);
+                        gs.x += dz.x; gs.y += dz.y; gs.z += dz.z; gs.w += dz.w;
+                    }
+                } else if (MODE == GT_MAX) {
+                    if (u[i].x > best.x) { best.x = u[i].x; bidx.x = k; }
+                    if (u[i].y > best.y) { best.y = u[i].y; bidx.y = k; }
+                    if (u[i].z > best.z) { best.z = u[i].z; bidx.z = k; }
+                    if (u[i].w > best.w) { best.w = u[i].w; bidx.w = k; }
+                } else if (MODE == GT_SCATTER) {
+                    PVec4<AT>::store(out + o, make_float4(am.x == k ? small.x : 0.f, am.y == k ? small.y : 0.f,
+                                                          am.z == k ? small.z : 0.f, am.w == k ? small.w : 0.f));
+                } else if (MODE == GT_COMBINE) {
+                    float4 y = u[i];
+                    if (am.x == k) y.x += small.x;
+                    if (am.y == k) y.y += small.y;
+                    if (am.z == k) y.z += small.z;
+                    if (am.w == k) y.w += small.w;
+                    PVec4<AT>::store(out + o, y);
+                    p0.x += y.x; p0.y += y.y; p0.z += y.z; p0.w += y.w;
+                }
+            }
+        }
+        if (MODE == GT_BWD_APPLY || MODE == GT_MAX) {          // combine the row lanes of this group
+            __syncthreads();
+            sh0[lane_r][ct] = (MODE == GT_MAX) ? best : gs;
+            if (MODE == GT_MAX) sh1[lane_r][ct] = make_float4(__int_as_float(bidx.x), __int_as_float(bidx.y),
+                                                              __int_as_float(bidx.z), __int_as_float(bidx.w));
+            __syncthreads();
+            if (lane_r == 0 && col_ok) {
+                if (MODE == GT_BWD_APPLY) {
+#pragma unroll
+                    for (int l = 1; l < GT_RL; ++l) {
+                        const float4 t = sh0[l][ct];
+                        gs.x += t.x; gs.y += t.y; gs.z += t.z; gs.w += t.w;
+                    }
+                    PVec4<AT>::store(reinterpret_cast<AT *>(A.small_out) + (size_t)g * C + col, gs);
+                } else {
+#pragma unroll
+                    for (int l = 1; l < GT_RL; ++l) {
+                        const float4 t = sh0[l][ct];
+                        const float4 ti = sh1[l][ct];
+                        const int i0 = __float_as_int(ti.x), i1 = __float_as_int(ti.y), i2 = __float_as_int(ti.z),
+                                  i3 = __float_as_int(ti.w);
+                        // first occurrence wins ties (rows are visited in increasing k within a lane)
+                        if (t.x > best.x || (t.x == best.x && i0 < bidx.x)) { best.x = t.x; bidx.x = i0; }
+                        if (t.y > best.y || (t.y == best.y && i1 < bidx.y)) { best.y = t.y; bidx.y = i1; }
+                        if (t.z > best.z || (t.z == best.z && i2 < bidx.z)) { best.z = t.z; bidx.z = i2; }
+                        if (t.w > best.w || (t.w == best.w && i3 < bidx.w)) { best.w = t.w; bidx.w = i3; }
+                    }
+                    PVec4<AT>::store(reinterpret_cast<AT *>(A.small_out) + (size_t)g * C + col, best);
+                    *reinterpret_cast<int4 *>(A.arg_out + (size_t)g * C + col) = bidx;
+                }
+            }
+        }
+    }
+    if (MODE == GT_STATS || MODE == GT_BWD_REDUCE || MODE == GT_COMBINE) {
+        __syncthreads();
+        sh0[lane_r][ct] = p0;
+        sh1[lane_r][ct] = p1;
+        __syncthreads();
+        if (lane_r == 0 && col_ok) {
+#pragma unroll
+            for (int l = 1; l < GT_RL; ++l) {
+                const float4 t = sh0[l][ct], t1 = sh1[l][ct];
+                p0.x += t.x; p0.y += t.y; p0.z += t.z; p0.w += t.w;
+                p1.x += t1.x; p1.y += t1.y; p1.z += t1.z; p1.w += t1.w;
+            }
+            if (MODE == GT_COMBINE) {
+                if (A.colsum) {
+                    atomicAdd(A.colsum + col, p0.x); atomicAdd(A.colsum + col + 1, p0.y);
+                    atomicAdd(A.colsum + col + 2, p0.z); atomicAdd(A.colsum + col + 3, p0.w);
+                }
+            } else {
+                *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 2 + 0) * C + col) = p0;
+                *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 2 + 1) * C + col) = p1;
+            }
+        }
+    }
+}
+
+template <typename AT, int MODE>
+static void launch_group_tile(const GroupTileArgs &A, cudaStream_t st) {
+    const int cthreads = A.C / 4;
+    int ct = cthreads <= 128 ? cthreads : 128;
+    if (cthreads > 128) {
+        for (int t = 128; t >= 32; t -= 32)
+            if (cthreads % t == 0) { ct = t; break; }
+    }
+    const dim3 block(ct, GT_RL), grid(div_up(A.Gt, A.gpc), div_up(cthreads, ct));
+    group_tile_kernel<AT, MODE><<<grid, block, 0, st>>>(A);
+}
+
+}  // namespace up3d
+
+using namespace up3d;
+
+static bool pn_aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+/* ---- first layer ---- */
+extern "C" int up3d_pn_conv1_stats(int R, int GK, const float *nb, const float *W1, const float *b1, float *partials,
+                                   int n_partials, up3d_stream_t stream) {
+    UP3D_CHECK_ARG(R > 0 && GK > 0 && R % GK == 0, "up3d_pn_conv1_stats: R must be a positive multiple of G*K");
+    UP3D_CHECK_ARG(nb && W1 && b1 && partials && n_partials > 0, "up3d_pn_conv1_stats: NULL pointer");
+    pn_conv1_stats_kernel<<<n_partials, PN_C1, 0, (cudaStream_t)stream>>>(R, GK, nb, W1, b1, partials);
+    UP3D_LAUNCH_OK("pn_conv1_stats_kernel");
+    return 0;
+}
+
+extern "C" int up3d_pn_conv1_bn_relu(int act_bf16, int R, int GK, const float *nb, const float *W1, const float *b1,
+                                     const float *stats, void *y1, up3d_stream_t stream) {
+    UP3D_CHECK_ARG(R > 0 && GK > 0 && R % GK == 0, "up3d_pn_conv1_bn_relu: R must be a positive multiple of G*K");
+    UP3D_CHECK_ARG(nb && W1 && b1 && stats && y1 && pn_aligned16(y1), "up3d_pn_conv1_bn_relu: NULL or misaligned pointer");
+    const int grid = min(div_up(R, PN_TILE), UP3D_NUM_SMS * 4);
+    if (act_bf16)
+        pn_conv1_bn_relu_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(R, GK, nb, W1, b1, stats, (__nv_bfloat16 *)y1);
+    else
+        pn_conv1_bn_relu_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(R, GK, nb, W1, b1, stats, (float *)y1);
+    UP3D_LAUNCH_OK("pn_conv1_bn_relu_kernel");
+    return 0;
+}
+
+extern "C" int up3d_pn_conv1_bwd(int act_bf16, int pass, int R, int GK, const float *nb, const float *W1, const float *b1,
+                                 const float *stats, const void *dy1, const float *sums, double count, float *partials,
+                                 int n_partials, float *gW1, float *gb1, up3d_stream_t stream) {
+    UP3D_CHECK_ARG(R > 0 && GK > 0 && R % GK == 0, "up3d_pn_conv1_bwd: R must be a positive multiple of G*K");
+    UP3D_CHECK_ARG(nb && W1 && b1 && stats && dy1 && n_partials > 0, "up3d_pn_conv1_bwd: NULL pointer");
+    UP3D_CHECK_ARG(pass == 0 ? partials != nullptr : (sums && gW1 && gb1 && count > 0), "up3d_pn_conv1_bwd: missing outputs for this pass");
+    const float inv_count = pass == 0 ? 0.f : (float)(1.0 / count);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PN_BWD(AT, P) pn_conv1_bwd_kernel<AT, P><<<n_partials, PN_C1, 0, st>>>(R, GK, nb, W1, b1, stats, (const AT *)dy1, sums, inv_count, partials, gW1, gb1)
+    if (act_bf16) { if (pass == 0) PN_BWD(__nv_bfloat16, 0); else PN_BWD(__nv_bfloat16, 1); }
+    else { if (pass == 0) PN_BWD(float, 0); else PN_BWD(float, 1); }
+#undef PN_BWD
+    UP3D_LAUNCH_OK("pn_conv1_bwd_kernel");
+    return 0;
+}
+
+extern "C" int up3d_bn_reduce_finalize(int n_partials, int C, const float *partials, float *sums, double count,
+                                       const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                                       float *running_var, int64_t *num_batches_tracked, float *stats, up3d_stream_t stream) {
+    UP3D_CHECK_ARG(n_partials > 0 && C > 0 && partials, "up3d_bn_reduce_finalize: bad arguments");
+    UP3D_CHECK_ARG(sums || stats, "up3d_bn_reduce_finalize: nothing to write");
+    UP3D_CHECK_ARG(!stats || (gamma && beta && count > 0), "up3d_bn_reduce_finalize: stats need gamma/beta/count");
+    UP3D_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "up3d_bn_reduce_finalize: running stats come in pairs");
+    bn_reduce_finalize_kernel<<<div_up(C, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        n_partials, C, partials, sums, count, gamma, beta, eps, momentum, running_mean, running_var,
+        (long long *)num_batches_tracked, stats);
+    UP3D_LAUNCH_OK("bn_reduce_finalize_kernel");
+    return 0;
+}
+
+/* ---- group-tile passes ---- */
+static int gt_common(const char *name, int Gt, int K, int C, int gpc) {
+    UP3D_CHECK_ARG(Gt > 0 && K > 0 && C > 0 && C % 4 == 0 && gpc > 0, "%s: bad sizes Gt=%d K=%d C=%d", name, Gt, K, C);
+    UP3D_CHECK_ARG(C / 4 <= 128 || (C / 4) % 32 == 0, "%s: C=%d not supported", name, C);
+    return 0;
+}
+
+#define GT_DISPATCH(MODE)                                         \
+    do {                                                          \
+        if (act_bf16) launch_group_tile<__nv_bfloat16, MODE>(A, (cudaStream_t)stream); \
+        else launch_group_tile<float, MODE>(A, (cudaStream_t)stream);                  \
+    } while (0)
+
+extern "C" int up3d_gbn_stats(int act_bf16, int Gt, int K, int C, int gpc, const void *zl, const float *gpart, const float *bias,
+                              float *partials, up3d_stream_t stream) {
+    if (int rc = gt_common("up3d_gbn_stats", Gt, K, C, gpc)) return rc;
+    UP3D_CHECK_ARG(zl && partials && pn_aligned16(zl) && pn_aligned16(gpart) && pn_aligned16(bias) && pn_aligned16(partials),
+                   "up3d_gbn_stats: NULL or misaligned pointer");
+    GroupTileArgs A{};
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = gpc; A.in0 = zl; A.gpart = gpart; A.bias = bias; A.partials = partials;
+    GT_DISPATCH(GT_STATS);
+    UP3D_LAUNCH_OK("group_tile_kernel<stats>");
+    return 0;
+}
+
+extern "C" int up3d_gbn_apply_relu(int act_bf16, int Gt, int K, int C, int gpc, const void *zl, const float *gpart,
+                                   const float *bias, const float *stats, void *y, up3d_stream_t stream) {
+    if (int rc = gt_common("up3d_gbn_apply_relu", Gt, K, C, gpc)) return rc;
+    UP3D_CHECK_ARG(zl && stats && y && pn_aligned16(zl) && pn_aligned16(gpart) && pn_aligned16(bias) && pn_aligned16(stats) &&
+                   pn_aligned16(y), "up3d_gbn_apply_relu: NULL or misaligned pointer");
+    GroupTileArgs A{};
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = gpc; A.in0 = zl; A.gpart = gpart; A.bias = bias; A.stats = stats; A.out = y;
+    GT_DISPATCH(GT_APPLY);
+    UP3D_LAUNCH_OK("group_tile_kernel<apply>");
+    return 0;
+}
+
+extern "C" int up3d_gbn_bwd_reduce(int act_bf16, int Gt, int K, int C, int gpc, const void *dy, const void *zl, const float *gpart,
+                                   const float *bias, const float *stats, float *partials, up3d_stream_t stream) {
+    if (int rc = gt_common("up3d_gbn_bwd_reduce", Gt, K, C, gpc)) return rc;
+    UP3D_CHECK_ARG(dy && zl && stats && partials && pn_aligned16(dy) && pn_aligned16(zl) && pn_aligned16(gpart) &&
+                   pn_aligned16(bias) && pn_aligned16(stats) && pn_aligned16(partials), "up3d_gbn_bwd_reduce: NULL or misaligned pointer");
+    GroupTileArgs A{};
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = gpc; A.in0 = dy; A.in1 = zl; A.gpart = gpart; A.bias = bias; A.stats = stats;
+    A.partials = partials;
+    GT_DISPATCH(GT_BWD_REDUCE);
+    UP3D_LAUNCH_OK("group_tile_kernel<bwd_reduce>");
+    return 0;
+}
+
+extern "C" int up3d_gbn_bwd_apply(int act_bf16, int Gt, int K, int C, int gpc, const void *dy, const void *zl, const float *gpart,
+                                  const float *bias, const float *stats, const float *sums, double count, void *dz,
+                                  void *dgroup, up3d_stream_t stream) {
+    if (int rc = gt_common("up3d_gbn_bwd_apply", Gt, K, C, gpc)) return rc;
+    UP3D_CHECK_ARG(count > 0, "up3d_gbn_bwd_apply: count must be positive");
+    UP3D_CHECK_ARG(dy && zl && stats && sums && dz && dgroup && pn_aligned16(dy) && pn_aligned16(zl) && pn_aligned16(gpart) &&
+                   pn_aligned16(bias) && pn_aligned16(stats) && pn_aligned16(sums) && pn_aligned16(dz) && pn_aligned16(dgroup),
+                   "up3d_gbn_bwd_apply: NULL or misaligned pointer");
+    GroupTileArgs A{};
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = gpc; A.in0 = dy; A.in1 = zl; A.gpart = gpart; A.bias = bias; A.stats = stats;
+    A.sums = sums; A.inv_count = (float)(1.0 / count); A.out = dz; A.small_out = dgroup;
+    GT_DISPATCH(GT_BWD_APPLY);
+    UP3D_LAUNCH_OK("group_tile_kernel<bwd_apply>");
+    return 0;
+}
+
+extern "C" int up3d_group_max(int act_bf16, int Gt, int K, int C, const void *x, void *out, int32_t *arg, up3d_stream_t stream) {
+    if (int rc = gt_common("up3d_group_max", Gt, K, C, 1)) return rc;
+    UP3D_CHECK_ARG(x && out && arg && pn_aligned16(x) && pn_aligned16(out) && pn_aligned16(arg), "up3d_group_max: NULL or misaligned pointer");
+    GroupTileArgs A{};
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = 1; A.in0 = x; A.small_out = out; A.arg_out = arg;
+    GT_DISPATCH(GT_MAX);
+    UP3D_LAUNCH_OK("group_tile_kernel<max>");
+    return 0;
+}
+
+extern "C" int up3d_group_max_scatter(int act_bf16, int Gt, int K, int C, const void *dpooled, const int32_t *arg, void *dx,
+                                      up3d_stream_t stream) {
+    if (int rc = gt_common("up3d_group_max_scatter", Gt, K, C, 1)) return rc;
+    UP3D_CHECK_ARG(dpooled && arg && dx && pn_aligned16(dpooled) && pn_aligned16(arg) && pn_aligned16(dx),
+                   "up3d_group_max_scatter: NULL or misaligned pointer");
+    GroupTileArgs A{};
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = 1; A.small_in = dpooled; A.arg = arg; A.out = dx;
+    GT_DISPATCH(GT_SCATTER);
+    UP3D_LAUNCH_OK("group_tile_kernel<scatter>");
+    return 0;
+}
+
+extern "C" int up3d_group_combine(int act_bf16, int Gt, int K, int C, int gpc, const void *dlocal, const void *dpooled,
+                                  const int32_t *arg, void *dx, float *colsum, up3d_stream_t stream) {
+    if (int rc = gt_common("up3d_group_combine", Gt, K, C, gpc)) return rc;
+    UP3D_CHECK_ARG(dlocal && dpooled && arg && dx && pn_aligned16(dlocal) && pn_aligned16(dpooled) && pn_aligned16(arg) &&
+                   pn_aligned16(dx), "up3d_group_combine: NULL or misaligned pointer");
+    GroupTileArgs A{};
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = gpc; A.in0 = dlocal; A.small_in = dpooled; A.arg = arg; A.out = dx; A.colsum = colsum;
+    GT_DISPATCH(GT_COMBINE);
+    UP3D_LAUNCH_OK("group_tile_kernel<combine>");
+    return 0;
+}

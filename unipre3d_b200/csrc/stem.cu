@@ -32,7 +32,11 @@ stem_group_stats_kernel(int HW, int Cc, int G, const float *__restrict__ image, 
         float s = 0.f, q = 0.f;
         for (int k = 0; k < cpg; ++k) {
             const float4 w = s_w[g * cpg + k];
-            const float v = sinf(fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w))));
+            // MUFU sine after an explicit reduction to [-pi, pi] (|arg| is O(1) here; abs error ~5e-7, averaged over
+            // the 2.6e5 samples of a group it is far below the statistics' own fp32 rounding)
+            float a = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
+            a = fmaf(-6.28318530717958647692f, rintf(a * 0.15915494309189533577f), a);
+            const float v = __sinf(a);
             s += v;
             q = fmaf(v, v, q);
         }

@@ -63,6 +63,20 @@ class ShadowWeights:
                 if m.bias is not None:
                     self.masters.append(m.bias)
                     self.shadows.append(m._b16)
+        self._add_pointwise_convs(module)
+
+    def _add_pointwise_convs(self, module: nn.Module) -> None:
+        """bf16 shadows of the mini-PointNet's 1x1 convolutions (consumed as GEMM operands by fused_pointnet.py)."""
+        from .backbone import Encoder
+        for enc in module.modules():
+            if not isinstance(enc, Encoder):
+                continue
+            for m in enc.modules():
+                if isinstance(m, nn.Conv1d) and m.kernel_size == (1,) and m.weight.is_cuda and m.bias is not None:
+                    m._w16 = m.weight.detach().to(torch.bfloat16)
+                    m._b16 = m.bias.detach().to(torch.bfloat16)
+                    self.masters += [m.weight, m.bias]
+                    self.shadows += [m._w16, m._b16]
 
     @torch.no_grad()
     def refresh(self) -> None:
