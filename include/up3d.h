@@ -250,15 +250,18 @@ UP3D_API int up3d_adamw_step(int n_tensors, int n_chunks, const int32_t *chunk_t
  * Mini-PointNet of the tokenizer (openpoints/models/backbone/transformer.py:210-243 `Encoder`): the memory-bound
  * passes around its four dense GEMMs.  Rows are (group, k): r = g*K + k, g < Gt = B*G, R = Gt*K.
  * act_bf16 selects the dtype of the (R,C) / (Gt,C) activations (0 float, 1 __nv_bfloat16); statistics, partial
- * sums and parameter gradients are fp32.  BatchNorm statistics are written as per-CTA partial sums
- * (n_partials, 2, C) and reduced in fp64 by up3d_bn_reduce_finalize (deterministic, no atomics).
+ * sums and parameter gradients are fp32.  BatchNorm statistics are written as per-CTA partial sums and merged in
+ * fp64 by up3d_bn_reduce_finalize / up3d_bn_reduce_sums (deterministic, no atomics).
  * stats (4,C) = batch mean, rstd, a = gamma*rstd, d = beta - mean*a.
  * ---------------------------------------------------------------------------------------- */
 
 /* first layer Conv1d(3,128) (transformer.py:215, 230): nb is the tokenizer's (B,3,G,K) neighbourhood tensor
- * (GK = G*K), W1 (128,3), b1 (128).  stats: partial sums of z = W1 x + b1 over n_partials CTAs. */
+ * (GK = G*K), W1 (128,3), b1 (128).  stats: one partial per tile of up3d_pn_stats_tile_rows() rows,
+ * partials (ceil(R/tile), 3, 128) = [shift, sum (z-shift), sum (z-shift)^2] of z = W1 x + b1 (shift = z of the
+ * tile's first row: no cancellation when |mean| >> std). */
+UP3D_API int up3d_pn_stats_tile_rows(void);
 UP3D_API int up3d_pn_conv1_stats(int R, int GK, const float *nb, const float *W1, const float *b1, float *partials,
-                                 int n_partials, up3d_stream_t stream);
+                                 up3d_stream_t stream);
 /* y1 (R,128) = ReLU(BatchNorm(W1 x + b1)) in one pass from the 3-channel input (transformer.py:215-217). */
 UP3D_API int up3d_pn_conv1_bn_relu(int act_bf16, int R, int GK, const float *nb, const float *W1, const float *b1,
                                    const float *stats, void *y1, up3d_stream_t stream);
@@ -269,15 +272,20 @@ UP3D_API int up3d_pn_conv1_bn_relu(int act_bf16, int R, int GK, const float *nb,
 UP3D_API int up3d_pn_conv1_bwd(int act_bf16, int pass, int R, int GK, const float *nb, const float *W1, const float *b1,
                                const float *stats, const void *dy1, const float *sums, double count, float *partials,
                                int n_partials, float *gW1, float *gb1, up3d_stream_t stream);
-/* partials (n_partials,2,C) -> sums (2,C) (may be NULL) and, when stats != NULL, the BatchNorm forward scalars
- * stats (4,C) for `count` samples plus nn.BatchNorm1d's running-statistics update (momentum, unbiased variance;
- * running_* and num_batches_tracked may be NULL). */
-UP3D_API int up3d_bn_reduce_finalize(int n_partials, int C, const float *partials, float *sums, double count,
+/* backward sums: partials (n_partials,2,C) -> sums (2,C), fp64 accumulation. */
+UP3D_API int up3d_bn_reduce_sums(int n_partials, int C, const float *partials, float *sums, up3d_stream_t stream);
+/* forward statistics: partials (n_partials,3,C) = [shift, sum (z-shift), sum (z-shift)^2], partial p covering
+ * min(rows_per_partial, total_rows - p*rows_per_partial) rows, merged pairwise in fp64 into the batch mean / M2 ->
+ * triple_out (3,C) = [mean, 0, M2] (same format: a second-level merge across ranks for SyncBatchNorm; may be NULL)
+ * and/or stats (4,C) plus nn.BatchNorm1d's running-statistics update (momentum, unbiased variance; running_* and
+ * num_batches_tracked may be NULL). */
+UP3D_API int up3d_bn_reduce_finalize(int n_partials, int C, const float *partials, int rows_per_partial, int64_t total_rows,
                                      const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
-                                     float *running_var, int64_t *num_batches_tracked, float *stats, up3d_stream_t stream);
+                                     float *running_var, int64_t *num_batches_tracked, float *triple_out, float *stats,
+                                     up3d_stream_t stream);
 /* BatchNorm over z = zl + gpart[g] + bias (zl (R,C): the local half of Conv1d(512,512) on [global || local]
  * (transformer.py:236-238); gpart (Gt,C) fp32: the global half, one row per group; both optional):
- *   stats      : partials (ceil(Gt/gpc), 2, C) of sum z, sum z^2
+ *   stats      : partials (ceil(Gt/gpc), 3, C) = [shift, sum (z-shift), sum (z-shift)^2], gpc*K rows per partial
  *   apply_relu : y (R,C) = ReLU(a z + d)
  *   bwd_reduce : partials of sum dy, sum dy*xhat (dy masked by the ReLU)
  *   bwd_apply  : dz (R,C) = a (dy - mean(dy) - xhat mean(dy xhat)) and dgroup (Gt,C) = sum_k dz (the gradient of gpart) */

@@ -57,10 +57,12 @@ def _load() -> C.CDLL:
         "up3d_gelu_bwd": (i32, [i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_scale_cast_colsum": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_stem_group_stats": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
-        "up3d_pn_conv1_stats": (i32, [i32, i32, vp, vp, vp, vp, i32, vp]),
+        "up3d_pn_stats_tile_rows": (i32, []),
+        "up3d_pn_conv1_stats": (i32, [i32, i32, vp, vp, vp, vp, vp]),
+        "up3d_bn_reduce_sums": (i32, [i32, i32, vp, vp, vp]),
         "up3d_pn_conv1_bn_relu": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, vp]),
         "up3d_pn_conv1_bwd": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, C.c_double, vp, i32, vp, vp, vp]),
-        "up3d_bn_reduce_finalize": (i32, [i32, i32, vp, vp, C.c_double, vp, vp, f32, f32, vp, vp, vp, vp, vp]),
+        "up3d_bn_reduce_finalize": (i32, [i32, i32, vp, i32, i64, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp]),
         "up3d_gbn_stats": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_gbn_apply_relu": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
         "up3d_gbn_bwd_reduce": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
@@ -87,7 +89,8 @@ EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_residen
             "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_focal_l2_loss",
             "up3d_raster_timing_enable", "up3d_raster_timing_read", "up3d_ln_fwd", "up3d_ln_bwd", "up3d_gelu_fwd",
             "up3d_gelu_bwd", "up3d_scale_cast_colsum", "up3d_adamw_chunk_elems", "up3d_adamw_step", "up3d_adamw_apply",
-            "up3d_grad_sumsq", "up3d_stem_group_stats", "up3d_pn_conv1_stats", "up3d_pn_conv1_bn_relu", "up3d_pn_conv1_bwd",
+            "up3d_grad_sumsq", "up3d_stem_group_stats", "up3d_pn_conv1_stats", "up3d_pn_stats_tile_rows",
+            "up3d_bn_reduce_sums", "up3d_pn_conv1_bn_relu", "up3d_pn_conv1_bwd",
             "up3d_bn_reduce_finalize", "up3d_gbn_stats", "up3d_gbn_apply_relu", "up3d_gbn_bwd_reduce", "up3d_gbn_bwd_apply",
             "up3d_group_max", "up3d_group_max_scatter", "up3d_group_combine"]
 

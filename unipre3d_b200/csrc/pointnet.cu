@@ -56,27 +56,29 @@ __device__ __forceinline__ void pn_load_x_tile(float (*xs)[PN_TILE], const float
     }
 }
 
-// partials (gridDim.x, 2, C1): per-CTA sum z, sum z^2 of z = W1 x + b1
+// partials (gridDim.x, 3, C1): per-CTA [shift, sum (z - shift), sum (z - shift)^2] of z = W1 x + b1 over the CTA's ONE
+// row tile (gridDim.x == ceil(R / PN_TILE)); shift = z of the tile's first row, so the sums carry no cancellation even
+// when |mean| >> std (merged in fp64 by bn_reduce_finalize_kernel).
 __global__ void __launch_bounds__(PN_C1)
 pn_conv1_stats_kernel(int R, int GK, const float *__restrict__ nb, const float *__restrict__ W1, const float *__restrict__ b1,
                       float *__restrict__ partials) {
     __shared__ float xs[3][PN_TILE];
     const int c = threadIdx.x;
     const float w0 = W1[3 * c], w1 = W1[3 * c + 1], w2 = W1[3 * c + 2], bb = b1[c];
+    const int r0 = blockIdx.x * PN_TILE;
+    pn_load_x_tile(xs, nb, R, GK, r0);
+    __syncthreads();
+    const int n = min(PN_TILE, R - r0);
+    const float shift = fmaf(w0, xs[0][0], fmaf(w1, xs[1][0], fmaf(w2, xs[2][0], bb)));
     float s = 0.f, q = 0.f;
-    for (int r0 = blockIdx.x * PN_TILE; r0 < R; r0 += gridDim.x * PN_TILE) {
-        __syncthreads();
-        pn_load_x_tile(xs, nb, R, GK, r0);
-        __syncthreads();
-        const int n = min(PN_TILE, R - r0);
-        for (int rr = 0; rr < n; ++rr) {
-            const float z = fmaf(w0, xs[0][rr], fmaf(w1, xs[1][rr], fmaf(w2, xs[2][rr], bb)));
-            s += z;
-            q = fmaf(z, z, q);
-        }
+    for (int rr = 0; rr < n; ++rr) {
+        const float z = fmaf(w0, xs[0][rr], fmaf(w1, xs[1][rr], fmaf(w2, xs[2][rr], bb))) - shift;
+        s += z;
+        q = fmaf(z, z, q);
     }
-    partials[((size_t)blockIdx.x * 2 + 0) * PN_C1 + c] = s;
-    partials[((size_t)blockIdx.x * 2 + 1) * PN_C1 + c] = q;
+    partials[((size_t)blockIdx.x * 3 + 0) * PN_C1 + c] = shift;
+    partials[((size_t)blockIdx.x * 3 + 1) * PN_C1 + c] = s;
+    partials[((size_t)blockIdx.x * 3 + 2) * PN_C1 + c] = q;
 }
 
 // y1[r, c] = relu(a[c] * (W1 x_r + b1)[c] + d[c]);  stats (4, C1): mean, rstd, a = gamma*rstd, d = beta - mean*a
@@ -160,43 +162,88 @@ pn_conv1_bwd_kernel(int R, int GK, const float *__restrict__ nb, const float *__
 }
 
 // ------------------------------------------------------------------------------------------ partial-sum reduction / BN finalize
-// partials (nPart, 2, C) -> sums (2, C) [fp64 accumulation]; when stats != NULL also the BatchNorm forward scalars
-// stats (4, C) = mean, rstd, a, d and the running-statistics update of nn.BatchNorm1d (momentum, unbiased variance).
 // grid = ceil(C / 32), block = (32, 8).
+// MODE 0 (backward sums): partials (nPart, 2, C) -> sums (2, C), fp64 accumulation.
+// MODE 1 (forward statistics): partials (nPart, 3, C) = [shift, sum (z-shift), sum (z-shift)^2] over
+//   n_p = min(rows_per_part, total_rows - p*rows_per_part) rows each, merged pairwise in fp64 (Chan et al.) into the batch
+//   mean and M2 -> optional triple_out (3, C) = [mean, 0, M2] (the same format, for a second-level merge across ranks)
+//   and/or stats (4, C) = mean, rstd, a = gamma*rstd, d = beta - mean*a plus nn.BatchNorm1d's running-statistics update
+//   (momentum, unbiased variance).
+struct MeanM2 { double n, mean, m2; };
+__device__ __forceinline__ void merge_mean_m2(MeanM2 &a, const MeanM2 &b) {
+    if (b.n <= 0.0) return;
+    if (a.n <= 0.0) { a = b; return; }
+    const double n = a.n + b.n, delta = b.mean - a.mean;
+    a.mean += delta * (b.n / n);
+    a.m2 += b.m2 + delta * delta * (a.n * b.n / n);
+    a.n = n;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
-bn_reduce_finalize_kernel(int nPart, int C, const float *__restrict__ partials, float *__restrict__ sums, double count,
-                          const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
-                          float *__restrict__ running_mean, float *__restrict__ running_var, long long *__restrict__ nbt,
-                          float *__restrict__ stats) {
-    __shared__ double sh[2][8][32];
+bn_reduce_finalize_kernel(int nPart, int C, const float *__restrict__ partials, float *__restrict__ sums, int rows_per_part,
+                          long long total_rows, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
+                          float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
+                          long long *__restrict__ nbt, float *__restrict__ triple_out, float *__restrict__ stats) {
+    __shared__ double sh[3][8][32];
     const int c = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
-    double s = 0.0, q = 0.0;
+    if (MODE == 0) {
+        double s = 0.0, q = 0.0;
+        if (c < C) {
+            for (int p = ly; p < nPart; p += 8) {
+                s += (double)partials[((size_t)p * 2 + 0) * C + c];
+                q += (double)partials[((size_t)p * 2 + 1) * C + c];
+            }
+        }
+        sh[0][ly][threadIdx.x] = s;
+        sh[1][ly][threadIdx.x] = q;
+        __syncthreads();
+        if (ly == 0 && c < C) {
+#pragma unroll
+            for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x]; q += sh[1][i][threadIdx.x]; }
+            sums[c] = (float)s;
+            sums[C + c] = (float)q;
+        }
+        return;
+    }
+    MeanM2 acc{0.0, 0.0, 0.0};
     if (c < C) {
         for (int p = ly; p < nPart; p += 8) {
-            s += (double)partials[((size_t)p * 2 + 0) * C + c];
-            q += (double)partials[((size_t)p * 2 + 1) * C + c];
+            const long long left = total_rows - (long long)p * rows_per_part;
+            const double n = (double)(left < rows_per_part ? (left > 0 ? left : 0) : rows_per_part);
+            if (n <= 0.0) continue;
+            const double shift = (double)partials[((size_t)p * 3 + 0) * C + c];
+            const double s = (double)partials[((size_t)p * 3 + 1) * C + c];
+            const double q = (double)partials[((size_t)p * 3 + 2) * C + c];
+            MeanM2 b{n, shift + s / n, q - s * s / n};
+            if (b.m2 < 0.0) b.m2 = 0.0;
+            merge_mean_m2(acc, b);
         }
     }
-    sh[0][ly][threadIdx.x] = s;
-    sh[1][ly][threadIdx.x] = q;
+    sh[0][ly][threadIdx.x] = acc.n;
+    sh[1][ly][threadIdx.x] = acc.mean;
+    sh[2][ly][threadIdx.x] = acc.m2;
     __syncthreads();
     if (ly == 0 && c < C) {
 #pragma unroll
-        for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x]; q += sh[1][i][threadIdx.x]; }
-        if (sums) { sums[c] = (float)s; sums[C + c] = (float)q; }
+        for (int i = 1; i < 8; ++i) merge_mean_m2(acc, MeanM2{sh[0][i][threadIdx.x], sh[1][i][threadIdx.x], sh[2][i][threadIdx.x]});
+        const double count = acc.n > 0.0 ? acc.n : 1.0;
+        if (triple_out) {
+            triple_out[c] = (float)acc.mean;
+            triple_out[C + c] = 0.f;
+            triple_out[2 * C + c] = (float)acc.m2;
+        }
         if (stats) {
-            const double mean = s / count;
-            double var = q / count - mean * mean;
-            if (var < 0.0) var = 0.0;
+            const double var = acc.m2 / count;
             const float rstd = (float)(1.0 / sqrt(var + (double)eps));
             const float a = gamma[c] * rstd;
-            stats[c] = (float)mean;
+            stats[c] = (float)acc.mean;
             stats[C + c] = rstd;
             stats[2 * C + c] = a;
-            stats[3 * C + c] = beta[c] - (float)mean * a;
+            stats[3 * C + c] = beta[c] - (float)acc.mean * a;
             if (running_mean) {
-                const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
-                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+                const double unbiased = count > 1.0 ? acc.m2 / (count - 1.0) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)acc.mean;
                 running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
             }
         }
@@ -260,6 +307,15 @@ group_tile_kernel(GroupTileArgs A) {
     }
     float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;       // per-CTA partial sums (STATS / BWD_REDUCE / COMBINE)
     const int g_begin = blockIdx.x * A.gpc, g_end = min(A.Gt, g_begin + A.gpc);
+    float4 shift = make_float4(0.f, 0.f, 0.f, 0.f);             // STATS: z of the CTA's first row (same for all row lanes)
+    if (MODE == GT_STATS && col_ok) {
+        shift = PVec4<AT>::load(in0 + (size_t)g_begin * K * C + col);
+        shift.x += bias.x; shift.y += bias.y; shift.z += bias.z; shift.w += bias.w;
+        if (A.gpart) {
+            const float4 t = *reinterpret_cast<const float4 *>(A.gpart + (size_t)g_begin * C + col);
+            shift.x += t.x; shift.y += t.y; shift.z += t.z; shift.w += t.w;
+        }
+    }
     for (int g = g_begin; g < g_end; ++g) {
         float4 gp = bias;                                         // broadcast term of this group: gpart + bias
         if (col_ok && A.gpart) {
@@ -294,7 +350,8 @@ group_tile_kernel(GroupTileArgs A) {
                 if (k >= K || !col_ok) continue;
                 const size_t o = ((size_t)g * K + k) * C + col;
                 if (MODE == GT_STATS) {
-                    const float z0 = u[i].x + gp.x, z1 = u[i].y + gp.y, z2 = u[i].z + gp.z, z3 = u[i].w + gp.w;
+                    const float z0 = u[i].x + gp.x - shift.x, z1 = u[i].y + gp.y - shift.y;
+                    const float z2 = u[i].z + gp.z - shift.z, z3 = u[i].w + gp.w - shift.w;
                     p0.x += z0; p0.y += z1; p0.z += z2; p0.w += z3;
                     p1.x = fmaf(z0, z0, p1.x); p1.y = fmaf(z1, z1, p1.y); p1.z = fmaf(z2, z2, p1.z); p1.w = fmaf(z3, z3, p1.w);
                 } else if (MODE == GT_APPLY) {
@@ -390,6 +447,10 @@ group_tile_kernel(GroupTileArgs A) {
                     atomicAdd(A.colsum + col, p0.x); atomicAdd(A.colsum + col + 1, p0.y);
                     atomicAdd(A.colsum + col + 2, p0.z); atomicAdd(A.colsum + col + 3, p0.w);
                 }
+            } else if (MODE == GT_STATS) {
+                *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 3 + 0) * C + col) = shift;
+                *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 3 + 1) * C + col) = p0;
+                *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 3 + 2) * C + col) = p1;
             } else {
                 *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 2 + 0) * C + col) = p0;
                 *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 2 + 1) * C + col) = p1;
@@ -417,11 +478,13 @@ using namespace up3d;
 static bool pn_aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 /* ---- first layer ---- */
+extern "C" int up3d_pn_stats_tile_rows(void) { return PN_TILE; }
+
 extern "C" int up3d_pn_conv1_stats(int R, int GK, const float *nb, const float *W1, const float *b1, float *partials,
-                                   int n_partials, up3d_stream_t stream) {
+                                   up3d_stream_t stream) {
     UP3D_CHECK_ARG(R > 0 && GK > 0 && R % GK == 0, "up3d_pn_conv1_stats: R must be a positive multiple of G*K");
-    UP3D_CHECK_ARG(nb && W1 && b1 && partials && n_partials > 0, "up3d_pn_conv1_stats: NULL pointer");
-    pn_conv1_stats_kernel<<<n_partials, PN_C1, 0, (cudaStream_t)stream>>>(R, GK, nb, W1, b1, partials);
+    UP3D_CHECK_ARG(nb && W1 && b1 && partials, "up3d_pn_conv1_stats: NULL pointer");
+    pn_conv1_stats_kernel<<<div_up(R, PN_TILE), PN_C1, 0, (cudaStream_t)stream>>>(R, GK, nb, W1, b1, partials);
     UP3D_LAUNCH_OK("pn_conv1_stats_kernel");
     return 0;
 }
@@ -455,17 +518,27 @@ extern "C" int up3d_pn_conv1_bwd(int act_bf16, int pass, int R, int GK, const fl
     return 0;
 }
 
-extern "C" int up3d_bn_reduce_finalize(int n_partials, int C, const float *partials, float *sums, double count,
+extern "C" int up3d_bn_reduce_sums(int n_partials, int C, const float *partials, float *sums, up3d_stream_t stream) {
+    UP3D_CHECK_ARG(n_partials > 0 && C > 0 && partials && sums, "up3d_bn_reduce_sums: bad arguments");
+    bn_reduce_finalize_kernel<0><<<div_up(C, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        n_partials, C, partials, sums, 0, 0, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
+    UP3D_LAUNCH_OK("bn_reduce_finalize_kernel<sums>");
+    return 0;
+}
+
+extern "C" int up3d_bn_reduce_finalize(int n_partials, int C, const float *partials, int rows_per_partial, int64_t total_rows,
                                        const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
-                                       float *running_var, int64_t *num_batches_tracked, float *stats, up3d_stream_t stream) {
-    UP3D_CHECK_ARG(n_partials > 0 && C > 0 && partials, "up3d_bn_reduce_finalize: bad arguments");
-    UP3D_CHECK_ARG(sums || stats, "up3d_bn_reduce_finalize: nothing to write");
-    UP3D_CHECK_ARG(!stats || (gamma && beta && count > 0), "up3d_bn_reduce_finalize: stats need gamma/beta/count");
+                                       float *running_var, int64_t *num_batches_tracked, float *triple_out, float *stats,
+                                       up3d_stream_t stream) {
+    UP3D_CHECK_ARG(n_partials > 0 && C > 0 && partials && rows_per_partial > 0 && total_rows > 0,
+                   "up3d_bn_reduce_finalize: bad arguments");
+    UP3D_CHECK_ARG(triple_out || stats, "up3d_bn_reduce_finalize: nothing to write");
+    UP3D_CHECK_ARG(!stats || (gamma && beta), "up3d_bn_reduce_finalize: stats need gamma/beta");
     UP3D_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "up3d_bn_reduce_finalize: running stats come in pairs");
-    bn_reduce_finalize_kernel<<<div_up(C, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
-        n_partials, C, partials, sums, count, gamma, beta, eps, momentum, running_mean, running_var,
-        (long long *)num_batches_tracked, stats);
-    UP3D_LAUNCH_OK("bn_reduce_finalize_kernel");
+    bn_reduce_finalize_kernel<1><<<div_up(C, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        n_partials, C, partials, nullptr, rows_per_partial, (long long)total_rows, gamma, beta, eps, momentum, running_mean,
+        running_var, (long long *)num_batches_tracked, triple_out, stats);
+    UP3D_LAUNCH_OK("bn_reduce_finalize_kernel<stats>");
     return 0;
 }
 

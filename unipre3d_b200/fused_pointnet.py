@@ -34,25 +34,29 @@ def _world(bn) -> int:
 
 
 def _reduce(partials, C):
-    """partials (n,2,C) -> sums (2,C), fp64 accumulation."""
+    """backward partials (n,2,C) -> sums (2,C), fp64 accumulation."""
     sums = torch.empty((2, C), dtype=torch.float32, device=partials.device)
-    check(_lib.lib.up3d_bn_reduce_finalize(partials.shape[0], C, ptr(partials), ptr(sums), 1.0, None, None, 0.0, 0.0, None,
-                                           None, None, None, stream_ptr()), 1)
+    check(_lib.lib.up3d_bn_reduce_sums(partials.shape[0], C, ptr(partials), ptr(sums), stream_ptr()), 1)
     return sums
 
 
-def _bn_forward_stats(partials, C, count, bn, world):
-    """partials of (sum z, sum z^2) -> stats (4,C) + running-statistics update; SyncBatchNorm: sums all-reduced."""
+def _bn_forward_stats(partials, C, rows_per_partial, rows, bn, world):
+    """shifted partials (n,3,C) -> stats (4,C) + running-statistics update.  SyncBatchNorm: every rank reduces its rows to
+    (mean, M2), the triples are all-gathered and merged again (the same pairwise fp64 merge)."""
+    L = _lib.lib
     stats = torch.empty((4, C), dtype=torch.float32, device=partials.device)
     mom = 0.1 if bn.momentum is None else float(bn.momentum)
     n = partials.shape[0]
     if world > 1:
-        partials = _reduce(partials, C)
-        dist.all_reduce(partials)
-        n, count = 1, count * world
-    check(_lib.lib.up3d_bn_reduce_finalize(n, C, ptr(partials), None, float(count), ptr(bn.weight), ptr(bn.bias),
-                                           float(bn.eps), mom, ptr(bn.running_mean), ptr(bn.running_var),
-                                           ptr(bn.num_batches_tracked), ptr(stats), stream_ptr()), 1)
+        local = torch.empty((3, C), dtype=torch.float32, device=partials.device)
+        check(L.up3d_bn_reduce_finalize(n, C, ptr(partials), rows_per_partial, rows, None, None, 0.0, 0.0, None, None, None,
+                                        ptr(local), None, stream_ptr()), 1)
+        partials = torch.empty((world, 3, C), dtype=torch.float32, device=local.device)
+        dist.all_gather_into_tensor(partials, local)
+        n, rows_per_partial, rows = world, rows, rows * world
+    check(L.up3d_bn_reduce_finalize(n, C, ptr(partials), rows_per_partial, rows, ptr(bn.weight), ptr(bn.bias), float(bn.eps),
+                                    mom, ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked), None,
+                                    ptr(stats), stream_ptr()), 1)
     return stats
 
 
@@ -91,10 +95,10 @@ class MiniPointNetFn(torch.autograd.Function):
         w1, wd1, wd2 = W1.detach().reshape(C1, 3).contiguous(), _world(meta.bn1), _world(meta.bn2)
         with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
             # ---- layer 1 (+BN+ReLU), computed from the 3-channel input
-            n1 = min((R + 127) // 128, 2 * _NUM_SMS)
-            part1 = torch.empty((n1, 2, C1), dtype=torch.float32, device=dev)
-            check(L.up3d_pn_conv1_stats(R, GK, ptr(nb), ptr(w1), ptr(b1), ptr(part1), n1, stream_ptr()), 1)
-            stats1 = _bn_forward_stats(part1, C1, R, meta.bn1, wd1)
+            tile = int(L.up3d_pn_stats_tile_rows())
+            part1 = torch.empty(((R + tile - 1) // tile, 3, C1), dtype=torch.float32, device=dev)
+            check(L.up3d_pn_conv1_stats(R, GK, ptr(nb), ptr(w1), ptr(b1), ptr(part1), stream_ptr()), 1)
+            stats1 = _bn_forward_stats(part1, C1, tile, R, meta.bn1, wd1)
             y1 = torch.empty((R, C1), dtype=act, device=dev)
             check(L.up3d_pn_conv1_bn_relu(fl, R, GK, ptr(nb), ptr(w1), ptr(b1), ptr(stats1), ptr(y1), stream_ptr()), 1)
             # ---- layer 2 + group max
@@ -111,9 +115,9 @@ class MiniPointNetFn(torch.autograd.Function):
             zl = f @ W3l.t()                                                        # (R, C3)
             gpc = 2 if Gt >= 4 * _NUM_SMS else 1
             n2 = (Gt + gpc - 1) // gpc
-            part2 = torch.empty((n2, 2, C3), dtype=torch.float32, device=dev)
+            part2 = torch.empty((n2, 3, C3), dtype=torch.float32, device=dev)
             check(L.up3d_gbn_stats(fl, Gt, K, C3, gpc, ptr(zl), ptr(gpart), ptr(b3), ptr(part2), stream_ptr()), 1)
-            stats2 = _bn_forward_stats(part2, C3, R, meta.bn2, wd2)
+            stats2 = _bn_forward_stats(part2, C3, gpc * K, R, meta.bn2, wd2)
             y3 = torch.empty((R, C3), dtype=act, device=dev)
             check(L.up3d_gbn_apply_relu(fl, Gt, K, C3, gpc, ptr(zl), ptr(gpart), ptr(b3), ptr(stats2), ptr(y3), stream_ptr()), 1)
             # ---- layer 4 + group max
