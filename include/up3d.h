@@ -218,6 +218,21 @@ UP3D_API int up3d_scale_cast_colsum(int act_bf16, int T, int L, int C, const flo
                                     float *dbias, up3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-head self-attention of the transformer Blocks (openpoints/models/backbone/transformer.py:36-77:
+ * softmax(q k^T * scale) v, no mask, attn_drop = 0), bf16 operands / fp32 accumulation, head_dim D = 64,
+ * L <= up3d_attn_max_len() tokens per sample.  qkv (B*L, 3*H*D) is the fused qkv GEMM output (q | k | v, heads
+ * contiguous inside each third, exactly the reshape(B,N,3,H,D) of transformer.py:58-62); o (B*L, H*D);
+ * lse (B,H,L) fp32 = log-sum-exp of the scaled scores (saved for the backward).
+ * Backward: dqkv (B*L, 3*H*D) from qkv, o, lse and do (B*L, H*D) in one launch (every output row owned by one CTA:
+ * deterministic, no atomics).
+ * ---------------------------------------------------------------------------------------- */
+UP3D_API int up3d_attn_max_len(void);
+UP3D_API int up3d_attn_fwd(int B, int L, int H, int D, float scale, const void *qkv, void *o, float *lse,
+                           up3d_stream_t stream);
+UP3D_API int up3d_attn_bwd(int B, int L, int H, int D, float scale, const void *qkv, const void *o, const float *lse,
+                           const void *dout, void *dqkv, up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimizer step of train_network.py:333-352: `_check_and_clip_gradients` (368-390: skip the step when any
  * gradient is NaN/Inf, else clip_grad_norm_(max_norm=1.0)) + torch.optim.AdamW(eps=1e-15) (156-159) in two
  * launches over a multi-tensor work list: sum of squares -> (coef, found_inf) -> one read-modify-write pass

@@ -312,3 +312,33 @@ def test_stem_field_group_stats_and_gather_match_dense():
     gb = torch.autograd.grad((b * w).sum(), list(conv.parameters()))
     for u, v in zip(ga, gb):
         assert torch.allclose(u, v, atol=1e-4 * float(v.abs().max()) + 1e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 129, 6), (1, 48, 2), (3, 100, 4), (1, 192, 1), (2, 17, 6)])
+def test_attention_kernels_match_fp32_reference(B, L, H):
+    """csrc/attention.cu against softmax(q k^T * scale) v evaluated in fp32 on the same bf16-rounded operands
+    (transformer.py:58-71), forward and backward (autograd of the fp32 formula)."""
+    from unipre3d_b200 import fused_encoder as fe
+    D = 64
+    C = H * D
+    torch.manual_seed(7)
+    qkv = (torch.randn(B * L, 3 * C, device=DEV) * 1.5).to(torch.bfloat16)
+    do = torch.randn(B * L, C, device=DEV).to(torch.bfloat16)
+    scale = D ** -0.5
+    assert fe.attn_supported(torch.bfloat16, L, D)
+    o, lse = fe.attn_fwd(qkv, B, L, H, D, scale)
+    ref_in = qkv.float().requires_grad_(True)
+    q, k, v = ref_in.view(B, L, 3, H, D).permute(2, 0, 3, 1, 4).unbind(0)
+    att = (q @ k.transpose(-2, -1)) * scale
+    ref_lse = torch.logsumexp(att, dim=-1)
+    ref_o = (att.softmax(dim=-1) @ v).transpose(1, 2).reshape(B * L, C)
+    assert torch.allclose(lse, ref_lse, atol=2e-3, rtol=1e-4)
+    assert float((o.float() - ref_o).abs().max()) <= 2e-2 * float(ref_o.abs().max()) + 1e-3
+    (ref_dqkv,) = torch.autograd.grad(ref_o, ref_in, do.float())
+    dqkv = fe.attn_bwd(qkv, o, lse, do, B, L, H, D, scale)
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        got, ref = dqkv[:, sl].float(), ref_dqkv[:, sl]
+        err = float((got - ref).abs().max())
+        assert err <= 3e-2 * float(ref.abs().max()) + 1e-3, (name, err, float(ref.abs().max()))
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+        assert cos > 0.999, (name, cos)

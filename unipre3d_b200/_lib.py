@@ -70,6 +70,9 @@ def _load() -> C.CDLL:
         "up3d_group_max": (i32, [i32, i32, i32, i32, vp, vp, vp, vp]),
         "up3d_group_max_scatter": (i32, [i32, i32, i32, i32, vp, vp, vp, vp]),
         "up3d_group_combine": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+        "up3d_attn_max_len": (i32, []),
+        "up3d_attn_fwd": (i32, [i32, i32, i32, i32, f32, vp, vp, vp, vp]),
+        "up3d_attn_bwd": (i32, [i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
         "up3d_adamw_chunk_elems": (i32, []),
         "up3d_adamw_step": (i32, [i32, i32] + [vp] * 10 + [f32] * 5 + [vp, vp]),
         "up3d_adamw_apply": (i32, [i32, i32] + [vp] * 10 + [f32] * 5 + [vp, vp]),
@@ -92,7 +95,8 @@ EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_residen
             "up3d_grad_sumsq", "up3d_stem_group_stats", "up3d_pn_conv1_stats", "up3d_pn_stats_tile_rows",
             "up3d_bn_reduce_sums", "up3d_pn_conv1_bn_relu", "up3d_pn_conv1_bwd",
             "up3d_bn_reduce_finalize", "up3d_gbn_stats", "up3d_gbn_apply_relu", "up3d_gbn_bwd_reduce", "up3d_gbn_bwd_apply",
-            "up3d_group_max", "up3d_group_max_scatter", "up3d_group_combine"]
+            "up3d_group_max", "up3d_group_max_scatter", "up3d_group_combine", "up3d_attn_max_len", "up3d_attn_fwd",
+            "up3d_attn_bwd"]
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0

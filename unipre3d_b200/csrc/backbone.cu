@@ -210,36 +210,42 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(size_t n4, const AT *__re
     }
 }
 
-// Column-threaded tile kernels: thread owns 4 consecutive columns, the CTA covers blockDim.x*4 columns and
-// `rows_per_cta` rows; per-thread column sums go out as 4 atomics per thread.
+// Column-threaded tile kernels: blockDim = (CT column threads, CL_LANES row lanes); a column thread owns 4 consecutive
+// columns, the CTA covers CT*4 columns x CL_LANES*CL_U rows; row lane l handles rows r0 + l + CL_LANES*u.  Column sums
+// are combined over the row lanes in shared memory, then ONE atomic per column per CTA (the atomics, not the data, bound
+// these kernels: T*C/(rows per CTA) of them).
 //   MODE 0: out = dy * gelu'(pre)                 (dy, pre: AT)          colsum(out) -> dbias
 //   MODE 1: out = scale[row / L] * g  (g: fp32)                           colsum(out) -> dbias
+constexpr int CL_LANES = 8, CL_U = 4, CL_MAX_CT = 64;
 template <typename AT, int MODE>
-__global__ void __launch_bounds__(256)
-col_tile_kernel(int T, int L, int Ccols, int rows_per_cta, const void *__restrict__ in0_, const AT *__restrict__ pre,
+__global__ void __launch_bounds__(CL_MAX_CT * CL_LANES)
+col_tile_kernel(int T, int L, int Ccols, const void *__restrict__ in0_, const AT *__restrict__ pre,
                 const float *__restrict__ scale, AT *__restrict__ out, float *__restrict__ dbias) {
-    const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-    if (col >= Ccols) return;
-    const int r0 = blockIdx.x * rows_per_cta, r1 = min(T, r0 + rows_per_cta);
+    __shared__ float4 s_acc[CL_LANES][CL_MAX_CT];
+    const int ct = threadIdx.x, lane_r = threadIdx.y;
+    const int col = (blockIdx.y * blockDim.x + ct) * 4;
+    const bool col_ok = col < Ccols;
+    const int r0 = blockIdx.x * (CL_LANES * CL_U);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    constexpr int U = 4;                       // rows in flight per thread: all loads of a batch are issued first
-    for (int rb = r0; rb < r1; rb += U) {
-        float4 a[U], p[U];
+    if (col_ok) {
+        float4 a[CL_U], p[CL_U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int row = min(rb + u, r1 - 1);
-            const size_t o = (size_t)row * Ccols + col;
-            if (MODE == 0) {
-                a[u] = Vec4<AT>::load(reinterpret_cast<const AT *>(in0_) + o);
-                p[u] = Vec4<AT>::load(pre + o);
-            } else {
-                a[u] = Vec4<float>::load(reinterpret_cast<const float *>(in0_) + o);
+        for (int u = 0; u < CL_U; ++u) {
+            const int row = r0 + lane_r + CL_LANES * u;
+            if (row < T) {
+                const size_t o = (size_t)row * Ccols + col;
+                if (MODE == 0) {
+                    a[u] = Vec4<AT>::load(reinterpret_cast<const AT *>(in0_) + o);
+                    p[u] = Vec4<AT>::load(pre + o);
+                } else {
+                    a[u] = Vec4<float>::load(reinterpret_cast<const float *>(in0_) + o);
+                }
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int row = rb + u;
-            if (row >= r1) break;
+        for (int u = 0; u < CL_U; ++u) {
+            const int row = r0 + lane_r + CL_LANES * u;
+            if (row >= T) continue;
             float4 q;
             if (MODE == 0) {
                 q = make_float4(a[u].x * gelu_grad_f(p[u].x), a[u].y * gelu_grad_f(p[u].y), a[u].z * gelu_grad_f(p[u].z),
@@ -253,7 +259,15 @@ col_tile_kernel(int T, int L, int Ccols, int rows_per_cta, const void *__restric
             acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
         }
     }
-    if (dbias) {
+    if (!dbias) return;                        // uniform over the CTA
+    s_acc[lane_r][ct] = acc;
+    __syncthreads();
+    if (lane_r == 0 && col_ok) {
+#pragma unroll
+        for (int l = 1; l < CL_LANES; ++l) {
+            const float4 t = s_acc[l][ct];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
         atomicAdd(dbias + col, acc.x); atomicAdd(dbias + col + 1, acc.y);
         atomicAdd(dbias + col + 2, acc.z); atomicAdd(dbias + col + 3, acc.w);
     }
@@ -409,7 +423,8 @@ template <typename AT>
 static int launch_ln_bwd(int NV, int T, int L, const void *dy, const float *xs, const float *mean, const float *rstd,
                          const float *gamma, const float *g_res, const float *scale, float *dx, float *dpos, void *dscaled,
                          float *dgamma, float *dbeta, float *dbias, cudaStream_t st) {
-    const int grid = min(div_up(T, LN_WARPS), UP3D_NUM_SMS);
+    // two rows per warp: the column-sum atomics (one per column, array and CTA) bound this kernel, not its 6 MB of data
+    const int grid = min(div_up(T, 2 * LN_WARPS), UP3D_NUM_SMS);
 #define LN_BWD_CASE(N)                                                                                              \
     case N:                                                                                                         \
         ln_bwd_kernel<AT, N><<<grid, LN_WARPS * 32, 0, st>>>(T, L, (const AT *)dy, xs, mean, rstd, gamma, g_res, scale, dx, \
@@ -482,19 +497,15 @@ extern "C" int up3d_gelu_fwd(int act_bf16, int64_t n, const void *x, void *y, up
 template <int MODE>
 static int launch_col_tile(int act_bf16, int T, int L, int C, const void *in0, const void *pre, const float *scale, void *out,
                            float *dbias, cudaStream_t st) {
-    int threads = 128;                       // largest warp multiple <= 256 dividing the C/4 column groups
-    for (int t = 256; t >= 32; t -= 32)
-        if ((C / 4) % t == 0) { threads = t; break; }
-    if (C / 4 < 32) threads = 32;
-    const int gy = div_up(C / 4, threads);
-    // ~4 resident CTAs per SM (latency hiding), at least 4 rows per CTA so the column-sum atomics stay few
-    int rows = max(4, div_up(T * gy, UP3D_NUM_SMS * 4));
-    const dim3 grid(div_up(T, rows), gy);
+    int ct = 32;                             // largest warp multiple <= CL_MAX_CT dividing the C/4 column groups
+    for (int t = CL_MAX_CT; t >= 32; t -= 32)
+        if ((C / 4) % t == 0) { ct = t; break; }
+    const dim3 block(ct, CL_LANES), grid(div_up(T, CL_LANES * CL_U), div_up(C / 4, ct));
     if (act_bf16)
-        col_tile_kernel<__nv_bfloat16, MODE><<<grid, threads, 0, st>>>(T, L, C, rows, in0, (const __nv_bfloat16 *)pre, scale,
-                                                                        (__nv_bfloat16 *)out, dbias);
+        col_tile_kernel<__nv_bfloat16, MODE><<<grid, block, 0, st>>>(T, L, C, in0, (const __nv_bfloat16 *)pre, scale,
+                                                                      (__nv_bfloat16 *)out, dbias);
     else
-        col_tile_kernel<float, MODE><<<grid, threads, 0, st>>>(T, L, C, rows, in0, (const float *)pre, scale, (float *)out, dbias);
+        col_tile_kernel<float, MODE><<<grid, block, 0, st>>>(T, L, C, in0, (const float *)pre, scale, (float *)out, dbias);
     return 0;
 }
 

@@ -162,88 +162,93 @@ pn_conv1_bwd_kernel(int R, int GK, const float *__restrict__ nb, const float *__
 }
 
 // ------------------------------------------------------------------------------------------ partial-sum reduction / BN finalize
-// grid = ceil(C / 32), block = (32, 8).
+// grid = ceil(C / 32), block = (32 columns, FIN_LANES lanes over the partials).
 // MODE 0 (backward sums): partials (nPart, 2, C) -> sums (2, C), fp64 accumulation.
 // MODE 1 (forward statistics): partials (nPart, 3, C) = [shift, sum (z-shift), sum (z-shift)^2] over
-//   n_p = min(rows_per_part, total_rows - p*rows_per_part) rows each, merged pairwise in fp64 (Chan et al.) into the batch
-//   mean and M2 -> optional triple_out (3, C) = [mean, 0, M2] (the same format, for a second-level merge across ranks)
-//   and/or stats (4, C) = mean, rstd, a = gamma*rstd, d = beta - mean*a plus nn.BatchNorm1d's running-statistics update
+//   n_p = min(rows_per_part, total_rows - p*rows_per_part) rows each.  Two passes in fp64, no cancellation:
+//     mean = sum_p (n_p shift_p + s_p) / N ;  M2 = sum_p [ q_p + 2 (shift_p - mean) s_p + n_p (shift_p - mean)^2 ]
+//   -> optional triple_out (3, C) = [mean, 0, M2] (the same format, for a second-level merge across ranks) and/or
+//   stats (4, C) = mean, rstd, a = gamma*rstd, d = beta - mean*a plus nn.BatchNorm1d's running-statistics update
 //   (momentum, unbiased variance).
-struct MeanM2 { double n, mean, m2; };
-__device__ __forceinline__ void merge_mean_m2(MeanM2 &a, const MeanM2 &b) {
-    if (b.n <= 0.0) return;
-    if (a.n <= 0.0) { a = b; return; }
-    const double n = a.n + b.n, delta = b.mean - a.mean;
-    a.mean += delta * (b.n / n);
-    a.m2 += b.m2 + delta * delta * (a.n * b.n / n);
-    a.n = n;
+constexpr int FIN_LANES = 32;
+
+__device__ __forceinline__ double fin_lane_sum(double v, double (*sh)[32]) {
+    __syncthreads();
+    sh[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < FIN_LANES; ++i) t += sh[i][threadIdx.x];
+    return t;                                   // every lane gets the column total
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * FIN_LANES)
 bn_reduce_finalize_kernel(int nPart, int C, const float *__restrict__ partials, float *__restrict__ sums, int rows_per_part,
                           long long total_rows, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
                           float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
                           long long *__restrict__ nbt, float *__restrict__ triple_out, float *__restrict__ stats) {
-    __shared__ double sh[3][8][32];
+    __shared__ double sh[FIN_LANES][32];
     const int c = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
+    const bool ok = c < C;
     if (MODE == 0) {
         double s = 0.0, q = 0.0;
-        if (c < C) {
-            for (int p = ly; p < nPart; p += 8) {
+        if (ok) {
+#pragma unroll 4
+            for (int p = ly; p < nPart; p += FIN_LANES) {
                 s += (double)partials[((size_t)p * 2 + 0) * C + c];
                 q += (double)partials[((size_t)p * 2 + 1) * C + c];
             }
         }
-        sh[0][ly][threadIdx.x] = s;
-        sh[1][ly][threadIdx.x] = q;
-        __syncthreads();
-        if (ly == 0 && c < C) {
-#pragma unroll
-            for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x]; q += sh[1][i][threadIdx.x]; }
+        s = fin_lane_sum(s, sh);
+        q = fin_lane_sum(q, sh);
+        if (ly == 0 && ok) {
             sums[c] = (float)s;
             sums[C + c] = (float)q;
         }
         return;
     }
-    MeanM2 acc{0.0, 0.0, 0.0};
-    if (c < C) {
-        for (int p = ly; p < nPart; p += 8) {
+    const double N = (double)total_rows;
+    double m = 0.0;
+    if (ok) {
+#pragma unroll 4
+        for (int p = ly; p < nPart; p += FIN_LANES) {
             const long long left = total_rows - (long long)p * rows_per_part;
             const double n = (double)(left < rows_per_part ? (left > 0 ? left : 0) : rows_per_part);
-            if (n <= 0.0) continue;
-            const double shift = (double)partials[((size_t)p * 3 + 0) * C + c];
-            const double s = (double)partials[((size_t)p * 3 + 1) * C + c];
-            const double q = (double)partials[((size_t)p * 3 + 2) * C + c];
-            MeanM2 b{n, shift + s / n, q - s * s / n};
-            if (b.m2 < 0.0) b.m2 = 0.0;
-            merge_mean_m2(acc, b);
+            m += n * (double)partials[((size_t)p * 3 + 0) * C + c] + (double)partials[((size_t)p * 3 + 1) * C + c];
         }
     }
-    sh[0][ly][threadIdx.x] = acc.n;
-    sh[1][ly][threadIdx.x] = acc.mean;
-    sh[2][ly][threadIdx.x] = acc.m2;
-    __syncthreads();
-    if (ly == 0 && c < C) {
-#pragma unroll
-        for (int i = 1; i < 8; ++i) merge_mean_m2(acc, MeanM2{sh[0][i][threadIdx.x], sh[1][i][threadIdx.x], sh[2][i][threadIdx.x]});
-        const double count = acc.n > 0.0 ? acc.n : 1.0;
+    const double mean = fin_lane_sum(m, sh) / N;
+    double m2 = 0.0;
+    if (ok) {
+#pragma unroll 4
+        for (int p = ly; p < nPart; p += FIN_LANES) {
+            const long long left = total_rows - (long long)p * rows_per_part;
+            const double n = (double)(left < rows_per_part ? (left > 0 ? left : 0) : rows_per_part);
+            const double dlt = (double)partials[((size_t)p * 3 + 0) * C + c] - mean;
+            m2 += (double)partials[((size_t)p * 3 + 2) * C + c] + 2.0 * dlt * (double)partials[((size_t)p * 3 + 1) * C + c] +
+                  n * dlt * dlt;
+        }
+    }
+    m2 = fin_lane_sum(m2, sh);
+    if (m2 < 0.0) m2 = 0.0;
+    if (ly == 0 && ok) {
         if (triple_out) {
-            triple_out[c] = (float)acc.mean;
+            triple_out[c] = (float)mean;
             triple_out[C + c] = 0.f;
-            triple_out[2 * C + c] = (float)acc.m2;
+            triple_out[2 * C + c] = (float)m2;
         }
         if (stats) {
-            const double var = acc.m2 / count;
+            const double var = m2 / N;
             const float rstd = (float)(1.0 / sqrt(var + (double)eps));
             const float a = gamma[c] * rstd;
-            stats[c] = (float)acc.mean;
+            stats[c] = (float)mean;
             stats[C + c] = rstd;
             stats[2 * C + c] = a;
-            stats[3 * C + c] = beta[c] - (float)acc.mean * a;
+            stats[3 * C + c] = beta[c] - (float)mean * a;
             if (running_mean) {
-                const double unbiased = count > 1.0 ? acc.m2 / (count - 1.0) : var;
-                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)acc.mean;
+                const double unbiased = N > 1.0 ? m2 / (N - 1.0) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
                 running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
             }
         }
@@ -520,7 +525,7 @@ extern "C" int up3d_pn_conv1_bwd(int act_bf16, int pass, int R, int GK, const fl
 
 extern "C" int up3d_bn_reduce_sums(int n_partials, int C, const float *partials, float *sums, up3d_stream_t stream) {
     UP3D_CHECK_ARG(n_partials > 0 && C > 0 && partials && sums, "up3d_bn_reduce_sums: bad arguments");
-    bn_reduce_finalize_kernel<0><<<div_up(C, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+    bn_reduce_finalize_kernel<0><<<div_up(C, 32), dim3(32, FIN_LANES), 0, (cudaStream_t)stream>>>(
         n_partials, C, partials, sums, 0, 0, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
     UP3D_LAUNCH_OK("bn_reduce_finalize_kernel<sums>");
     return 0;
@@ -535,7 +540,7 @@ extern "C" int up3d_bn_reduce_finalize(int n_partials, int C, const float *parti
     UP3D_CHECK_ARG(triple_out || stats, "up3d_bn_reduce_finalize: nothing to write");
     UP3D_CHECK_ARG(!stats || (gamma && beta), "up3d_bn_reduce_finalize: stats need gamma/beta");
     UP3D_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "up3d_bn_reduce_finalize: running stats come in pairs");
-    bn_reduce_finalize_kernel<1><<<div_up(C, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+    bn_reduce_finalize_kernel<1><<<div_up(C, 32), dim3(32, FIN_LANES), 0, (cudaStream_t)stream>>>(
         n_partials, C, partials, nullptr, rows_per_partial, (long long)total_rows, gamma, beta, eps, momentum, running_mean,
         running_var, (long long *)num_batches_tracked, triple_out, stats);
     UP3D_LAUNCH_OK("bn_reduce_finalize_kernel<stats>");

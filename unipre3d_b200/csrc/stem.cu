@@ -13,34 +13,45 @@ namespace up3d {
 
 constexpr int STEM_MAX_C = 256;
 
-// grid (ceil(HW / 256), n), block 256: thread = pixel.  sums (n, G, 2) fp64: [sum f, sum f^2] over the group's
-// channels and all pixels.
+// grid (ceil(HW / (256*STEM_PIX)), n), block 256: a thread accumulates STEM_PIX pixels (stride 256: coalesced) before
+// the warp reduction, so the shuffles / shared atomics are amortised.  sums (n, G, 2) fp64: [sum f, sum f^2] over the
+// group's channels and all pixels.
+constexpr int STEM_PIX = 8;
 __global__ void __launch_bounds__(256)
 stem_group_stats_kernel(int HW, int Cc, int G, const float *__restrict__ image, const float *__restrict__ proj,
                         const float *__restrict__ shift, double *__restrict__ sums) {
     __shared__ float4 s_w[STEM_MAX_C];          // proj row + shift
     __shared__ float s_acc[2 * STEM_MAX_C];     // per group: sum, sum of squares (G <= C)
-    const int n = blockIdx.y, pix = blockIdx.x * 256 + threadIdx.x;
+    const int n = blockIdx.y, pix0 = blockIdx.x * (256 * STEM_PIX) + threadIdx.x;
     for (int c = threadIdx.x; c < Cc; c += 256) s_w[c] = make_float4(proj[3 * c], proj[3 * c + 1], proj[3 * c + 2], shift[c]);
     for (int i = threadIdx.x; i < 2 * G; i += 256) s_acc[i] = 0.f;
     __syncthreads();
-    const bool valid = pix < HW;
     const float *img = image + (size_t)n * 3 * HW;
-    const float x0 = valid ? img[pix] : 0.f, x1 = valid ? img[HW + pix] : 0.f, x2 = valid ? img[2 * HW + pix] : 0.f;
+    float x0[STEM_PIX], x1[STEM_PIX], x2[STEM_PIX];
+    int n_valid = 0;
+#pragma unroll
+    for (int j = 0; j < STEM_PIX; ++j) {
+        const int pix = pix0 + 256 * j;
+        const bool valid = pix < HW;
+        x0[j] = valid ? img[pix] : 0.f; x1[j] = valid ? img[HW + pix] : 0.f; x2[j] = valid ? img[2 * HW + pix] : 0.f;
+        n_valid += valid ? 1 : 0;               // valid pixels are a prefix of j
+    }
     const int cpg = Cc / G;
     for (int g = 0; g < G; ++g) {
         float s = 0.f, q = 0.f;
         for (int k = 0; k < cpg; ++k) {
             const float4 w = s_w[g * cpg + k];
-            // MUFU sine after an explicit reduction to [-pi, pi] (|arg| is O(1) here; abs error ~5e-7, averaged over
-            // the 2.6e5 samples of a group it is far below the statistics' own fp32 rounding)
-            float a = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
-            a = fmaf(-6.28318530717958647692f, rintf(a * 0.15915494309189533577f), a);
-            const float v = __sinf(a);
-            s += v;
-            q = fmaf(v, v, q);
+#pragma unroll
+            for (int j = 0; j < STEM_PIX; ++j) {
+                // MUFU sine after an explicit reduction to [-pi, pi] (|arg| is O(1) here; abs error ~5e-7, averaged
+                // over the 2.6e5 samples of a group it is far below the statistics' own fp32 rounding)
+                float a = fmaf(w.x, x0[j], fmaf(w.y, x1[j], fmaf(w.z, x2[j], w.w)));
+                a = fmaf(-6.28318530717958647692f, rintf(a * 0.15915494309189533577f), a);
+                const float v = j < n_valid ? __sinf(a) : 0.f;
+                s += v;
+                q = fmaf(v, v, q);
+            }
         }
-        if (!valid) s = q = 0.f;
         s = warp_sum(s);
         q = warp_sum(q);
         if ((threadIdx.x & 31) == 0) {
@@ -66,7 +77,7 @@ extern "C" int up3d_stem_group_stats(int n_images, int H, int W, int C, int G, c
     cudaStream_t st = (cudaStream_t)stream;
     UP3D_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * G * (size_t)n_images, st));
     const int HW = H * W;
-    stem_group_stats_kernel<<<dim3(div_up(HW, 256), n_images), 256, 0, st>>>(HW, C, G, image, proj, shift, sums);
+    stem_group_stats_kernel<<<dim3(div_up(HW, 256 * STEM_PIX), n_images), 256, 0, st>>>(HW, C, G, image, proj, shift, sums);
     UP3D_LAUNCH_OK("stem_group_stats_kernel");
     return 0;
 }

@@ -5,14 +5,16 @@ x + drop_path(mlp(norm2(x)))) inside TransformerEncoder.forward's `x = block(x +
 (36-77) and Mlp (10-33).  The eager module graph spends ~60 launches per Block and step on 1.5 MB tensors; here each
 Block is 8 launches forward and ~17 backward:
 
-    forward   ln_fwd (residual + DropPath scale + pos + LayerNorm, one pass) -> qkv GEMM -> SDPA -> proj GEMM(+bias)
+    forward   ln_fwd (residual + DropPath scale + pos + LayerNorm, one pass) -> qkv GEMM -> attention -> proj GEMM(+bias)
               -> ln_fwd -> fc1 GEMM(+bias) -> gelu_fwd -> fc2 GEMM(+bias)
     backward  2 GEMMs per Linear (dX in the activation dtype, dW written in fp32 by the GEMM), gelu_bwd (+ fc1 bias
               gradient), ln_bwd (+ residual add, LayerNorm parameter gradients, dpos accumulation, DropPath scale,
               cast and the bias gradient of the Linear in front -- all in the same pass), SDPA backward.
 
 The hand-written passes are libunipre3d_b200's up3d_ln_fwd / up3d_ln_bwd / up3d_gelu_* / up3d_scale_cast_colsum
-(csrc/backbone.cu); the dense GEMMs and the fused attention are library calls (cuBLASLt / cuDNN).  The residual
+(csrc/backbone.cu) and up3d_attn_fwd / up3d_attn_bwd (csrc/attention.cu: bf16 operands, 1 launch each way, reading
+the qkv GEMM output and writing the dqkv GEMM input in place); the dense GEMMs are library calls (cuBLASLt), as is
+the attention of the fp32 reference-precision mode (torch SDPA).  The residual
 stream, LayerNorm statistics and all parameter gradients are fp32; GEMM operands are fp32 (reference precision) or
 bf16 (tensor cores, persistent bf16 weight shadows from mixed_precision.ShadowWeights).
 """
@@ -27,6 +29,7 @@ from . import _lib
 from ._lib import check, ptr, require_cuda, stream_ptr
 
 _KEEP_CACHE = {}
+SAVED_PER_BLOCK = 13    # xs, y1, mean1, rstd1, o, x2, y2, mean2, rstd2, pre, h, qkv, lse
 PARAMS_PER_BLOCK = 11   # norm1.w, norm1.b, qkv.w, proj.w, proj.b, norm2.w, norm2.b, fc1.w, fc1.b, fc2.w, fc2.b
 
 
@@ -77,6 +80,25 @@ def scale_cast_colsum(g, scale, L, act_dtype, dbias):
     return out
 
 
+def attn_supported(act_dtype, L, D) -> bool:
+    return act_dtype == torch.bfloat16 and D == 64 and L <= int(_lib.lib.up3d_attn_max_len())
+
+
+def attn_fwd(qkv, B, L, H, D, scale):
+    """qkv (B*L, 3*H*D) bf16 -> o (B*L, H*D) bf16, lse (B,H,L) fp32 (csrc/attention.cu)."""
+    o = torch.empty((B * L, H * D), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((B, H, L), dtype=torch.float32, device=qkv.device)
+    check(_lib.lib.up3d_attn_fwd(B, L, H, D, float(scale), ptr(qkv), ptr(o), ptr(lse), stream_ptr()), launches=1)
+    return o, lse
+
+
+def attn_bwd(qkv, o, lse, do, B, L, H, D, scale):
+    dqkv = torch.empty_like(qkv)
+    check(_lib.lib.up3d_attn_bwd(B, L, H, D, float(scale), ptr(qkv), ptr(o), ptr(lse), ptr(do), ptr(dqkv), stream_ptr()),
+          launches=1)
+    return dqkv
+
+
 def _wgrad(dy, x):
     """dW = dy^T @ x written in fp32 by the GEMM itself (no cast pass for the fp32 master gradient)."""
     if dy.dtype == torch.float32:
@@ -104,6 +126,7 @@ class EncoderStackFn(torch.autograd.Function):
         pos2 = pos.reshape(T, C).contiguous().float()
         pend, pend_scale = None, None
         saved, attn_nodes = [], []
+        own_attn = attn_supported(act, L, D)
         with torch.cuda.device(x.device), torch.autocast("cuda", enabled=False):
             for i in range(depth):
                 n1w, n1b, _, _, _, n2w, n2b, _, _, _, _ = params[i * PARAMS_PER_BLOCK:(i + 1) * PARAMS_PER_BLOCK]
@@ -112,22 +135,26 @@ class EncoderStackFn(torch.autograd.Function):
                 s2 = masks[2 * i + 1] if masks is not None else None
                 xs, y1, mu1, rs1 = ln_fwd(xcur, pend, pend_scale, pos2, n1w, n1b, meta.eps1[i], L, act)
                 qkv = y1 @ wqkv.t()
-                with torch.enable_grad():
-                    qkv_l = qkv.detach().requires_grad_(True)
-                    q, k, v = qkv_l.view(B, L, 3, H, D).permute(2, 0, 3, 1, 4).unbind(0)
-                    o4 = F.scaled_dot_product_attention(q, k, v, scale=meta.scale)
-                    o_l = o4.transpose(1, 2).reshape(T, C)
-                o = o_l.detach()
+                if own_attn:
+                    o, lse = attn_fwd(qkv, B, L, H, D, meta.scale)
+                    attn_nodes.append(None)
+                else:                                   # fp32 operands (reference precision): library SDPA
+                    with torch.enable_grad():
+                        qkv_l = qkv.detach().requires_grad_(True)
+                        q, k, v = qkv_l.view(B, L, 3, H, D).permute(2, 0, 3, 1, 4).unbind(0)
+                        o4 = F.scaled_dot_product_attention(q, k, v, scale=meta.scale)
+                        o_l = o4.transpose(1, 2).reshape(T, C)
+                    o, lse = o_l.detach(), mu1.new_empty(0)
+                    attn_nodes.append((qkv_l, o_l))
                 a = F.linear(o, wproj, bproj)
                 x2, y2, mu2, rs2 = ln_fwd(xs, a, s1, None, n2w, n2b, meta.eps2[i], L, act)
                 pre = F.linear(y2, w1, b1)
                 h = gelu_fwd(pre)
                 d = F.linear(h, w2, b2)
-                saved += [xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h]
-                attn_nodes.append((qkv_l, o_l))
+                saved += [xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h, qkv, lse]
                 xcur, pend, pend_scale = x2, d, s2
             out, _, _, _ = ln_fwd(xcur, pend, pend_scale, None, None, None, 0.0, L, act, want_y=False)
-        ctx.meta, ctx.depth, ctx.attn_nodes = meta, depth, attn_nodes
+        ctx.meta, ctx.depth, ctx.attn_nodes, ctx.own_attn = meta, depth, attn_nodes, own_attn
         ctx.has_masks = masks is not None
         ctx.save_for_backward(*(saved + list(params) + ([masks] if masks is not None else [])))
         return out.view(B, L, C)
@@ -138,7 +165,8 @@ class EncoderStackFn(torch.autograd.Function):
         B, L, C = meta.B, meta.L, meta.C
         T, act = B * L, meta.act_dtype
         sv = ctx.saved_tensors
-        n_act = 11 * depth
+        n_act = SAVED_PER_BLOCK * depth
+        H, D = meta.heads, C // meta.heads
         params = sv[n_act:n_act + PARAMS_PER_BLOCK * depth]
         masks = sv[-1] if ctx.has_masks else None
         Hd = meta.compute_weights[0][3].shape[0]
@@ -159,7 +187,7 @@ class EncoderStackFn(torch.autograd.Function):
             s2_last = masks[2 * depth - 1] if masks is not None else None
             dd = scale_cast_colsum(g, s2_last, L, act, sm(depth - 1, 5))
             for i in range(depth - 1, -1, -1):
-                xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h = sv[11 * i:11 * i + 11]
+                xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h, qkv, lse = sv[SAVED_PER_BLOCK * i:SAVED_PER_BLOCK * (i + 1)]
                 n1w, _, _, _, _, n2w, _, _, _, _, _ = params[i * PARAMS_PER_BLOCK:(i + 1) * PARAMS_PER_BLOCK]
                 wqkv, wproj, _, w1, _, w2, _ = meta.compute_weights[i]
                 s1 = masks[2 * i] if masks is not None else None
@@ -174,9 +202,12 @@ class EncoderStackFn(torch.autograd.Function):
                 # ---- attention branch
                 do = da @ wproj
                 gwproj = _wgrad(da, o)
-                qkv_l, o_l = ctx.attn_nodes[i]
-                (dqkv,) = torch.autograd.grad(o_l, qkv_l, do)
-                dqkv = dqkv.contiguous()
+                if ctx.own_attn:
+                    dqkv = attn_bwd(qkv, o, lse, do, B, L, H, D, meta.scale)
+                else:
+                    qkv_l, o_l = ctx.attn_nodes[i]
+                    (dqkv,) = torch.autograd.grad(o_l, qkv_l, do)
+                    dqkv = dqkv.contiguous()
                 dy1 = dqkv @ wqkv
                 gwqkv = _wgrad(dqkv, y1)
                 g, dd = ln_bwd(dy1, xs, mu1, rs1, n1w, dx2, s2_prev, L, dpos, i > 0, sm(i, 0), sm(i, 1),
