@@ -36,6 +36,8 @@ constexpr int AT_MAX_L = 192;
 
 __host__ __device__ inline int at_round16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline size_t at_align128(size_t x) { return (x + 127) & ~(size_t)127; }
+// fp32 staging regions hold the (48 x Lp) score tile (ld Lp+4) and later the (48 x 64) output tile (ld AT_OLD)
+__host__ __device__ inline int at_stage_ld(int Lp) { return Lp + 4 > 68 ? Lp + 4 : 68; }
 // rows of the full-(b,h) operand tiles in shared memory: every 48-row tile must be addressable (zero-filled past L)
 __host__ __device__ inline int at_rows(int L) { const int a = at_round16(L), b = (L + AT_QT - 1) / AT_QT * AT_QT; return a > b ? a : b; }
 
@@ -110,7 +112,7 @@ struct AttnSmemFwd {
         k = o; o = at_align128(o + (size_t)Lp * AT_LD * 2);
         v = o; o = at_align128(o + (size_t)Lp * AT_LD * 2);
         q = o; o = at_align128(o + (size_t)AT_QT * AT_LD * 2);
-        s = o; o = at_align128(o + (size_t)AT_QT * (Lp + 4) * 4);
+        s = o; o = at_align128(o + (size_t)AT_QT * at_stage_ld(Lp) * 4);
         p = o; o = at_align128(o + (size_t)AT_QT * (Lp + 8) * 2);
         rowinv = o; o = at_align128(o + AT_QT * 4);
         total = o;
@@ -173,8 +175,8 @@ struct AttnSmemBwd {
         dO = o; o = at_align128(o + (size_t)Lr * AT_LD * 2);
         lse = o; o = at_align128(o + (size_t)Lp * 4);
         delta = o; o = at_align128(o + (size_t)Lp * 4);
-        s = o; o = at_align128(o + (size_t)AT_QT * (Lp + 4) * 4);
-        dp = o; o = at_align128(o + (size_t)AT_QT * (Lp + 4) * 4);
+        s = o; o = at_align128(o + (size_t)AT_QT * at_stage_ld(Lp) * 4);
+        dp = o; o = at_align128(o + (size_t)AT_QT * at_stage_ld(Lp) * 4);
         p = o; o = at_align128(o + (size_t)AT_QT * (Lp + 8) * 2);
         ds = o; o = at_align128(o + (size_t)AT_QT * (Lp + 8) * 2);
         total = o;
