@@ -31,7 +31,8 @@ constexpr int AT_D = 64;          // head dim
 constexpr int AT_QT = 48;         // rows per CTA tile (3 row strips of 16)
 constexpr int AT_LD = 72;         // bf16 row stride of the (rows, 64) operand tiles (64 + 8 pad: 144 B, 32 B-aligned tiles)
 constexpr int AT_OLD = 68;        // fp32 row stride of the (48, 64) output staging tiles
-constexpr int AT_THREADS = 192;   // 6 warps: (row strip wr = warp % 3, half wh = warp / 3)
+constexpr int AT_THREADS = 384;   // 12 warps: (row strip wr = warp % 3, column quarter wq = warp / 3); the kernels are
+                                  // latency-bound chains of fragment loads and MMAs, so warps per SM matter more than tile reuse
 constexpr int AT_MAX_L = 192;
 
 __host__ __device__ inline int at_round16(int x) { return (x + 15) & ~15; }
@@ -41,53 +42,62 @@ __host__ __device__ inline int at_stage_ld(int Lp) { return Lp + 4 > 68 ? Lp + 4
 // rows of the full-(b,h) operand tiles in shared memory: every 48-row tile must be addressable (zero-filled past L)
 __host__ __device__ inline int at_rows(int L) { const int a = at_round16(L), b = (L + AT_QT - 1) / AT_QT * AT_QT; return a > b ? a : b; }
 
-// (rows x 64) bf16 tile of a (T, row_stride) matrix -> shared [Lp][AT_LD]; rows >= n_valid are zero-filled
+// (rows x 64) bf16 tile of a (T, row_stride) matrix -> shared [n_rows][AT_LD]; rows >= n_valid are zero-filled.
+// Asynchronous 16-byte copies (cp.async, no register staging): a thread issues all of its copies back to back, so the
+// whole tile is in flight at once; the caller waits with at_async_wait() + __syncthreads().
 __device__ __forceinline__ void at_load_rows(bf16 *dst, const bf16 *src, size_t row_stride, int row0, int n_valid, int n_rows) {
     for (int i = threadIdx.x; i < n_rows * 8; i += AT_THREADS) {
         const int r = i >> 3, ch = i & 7;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < n_valid) v = *reinterpret_cast<const uint4 *>(src + (size_t)(row0 + r) * row_stride + ch * 8);
-        *reinterpret_cast<uint4 *>(dst + r * AT_LD + ch * 8) = v;
+        const bool ok = r < n_valid;
+        const bf16 *g = ok ? src + (size_t)(row0 + r) * row_stride + ch * 8 : src;
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * AT_LD + ch * 8);
+        const int nbytes = ok ? 16 : 0;              // src-size 0: the 16 destination bytes are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(g), "r"(nbytes) : "memory");
     }
 }
+__device__ __forceinline__ void at_async_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// out (48 x Lp, fp32, ld = ldS) = X (48 x 64 rows of Xs starting at x_row0) * Y^T (Y: Lp x 64), both [.][AT_LD] bf16
-__device__ __forceinline__ void at_gemm_xyT(float *out, int ldS, const bf16 *Xs, int x_row0, const bf16 *Ys, int Lp, int wr, int wh) {
+// out (48 x Lp, fp32, ld = ldS) = X (48 x 64 rows of Xs starting at x_row0) * Y^T (Y: Lp x 64), both [.][AT_LD] bf16;
+// this warp: row strip wr, column tiles ct = wq, wq+4, ...
+__device__ __forceinline__ void at_gemm_xyT(float *out, int ldS, const bf16 *Xs, int x_row0, const bf16 *Ys, int Lp, int wr, int wq) {
     wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> a[4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) wmma::load_matrix_sync(a[ks], Xs + (x_row0 + wr * 16) * AT_LD + ks * 16, AT_LD);
-    const int nct = Lp / 16, half = (nct + 1) / 2;
-    const int c_begin = wh ? half : 0, c_end = wh ? nct : half;
-    for (int ct = c_begin; ct < c_end; ++ct) {
+    const int nct = Lp / 16;
+    for (int ct = wq; ct < nct; ct += 4) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::col_major> b[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) wmma::load_matrix_sync(b[ks], Ys + ct * 16 * AT_LD + ks * 16, AT_LD);
         wmma::fragment<wmma::accumulator, 16, 16, 16, float> c;
         wmma::fill_fragment(c, 0.f);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::col_major> b;
-            wmma::load_matrix_sync(b, Ys + ct * 16 * AT_LD + ks * 16, AT_LD);
-            wmma::mma_sync(c, a[ks], b, c);
-        }
+        for (int ks = 0; ks < 4; ++ks) wmma::mma_sync(c, a[ks], b[ks], c);
         wmma::store_matrix_sync(out + wr * 16 * ldS + ct * 16, c, ldS, wmma::mem_row_major);
     }
 }
 
 // out (48 x 64, fp32, ld = AT_OLD) = P (48 x Lp bf16, ld = ldP) * Y (Lp x 64, [.][AT_LD] bf16); this warp: row strip wr,
-// column tiles 2*wh and 2*wh+1
-__device__ __forceinline__ void at_gemm_py(float *out, const bf16 *Ps, int ldP, const bf16 *Ys, int Lp, int wr, int wh) {
+// column tile wq; two independent accumulators (even / odd k-steps) shorten the MMA dependency chain
+__device__ __forceinline__ void at_gemm_py(float *out, const bf16 *Ps, int ldP, const bf16 *Ys, int Lp, int wr, int wq) {
     wmma::fragment<wmma::accumulator, 16, 16, 16, float> c0, c1;
     wmma::fill_fragment(c0, 0.f);
     wmma::fill_fragment(c1, 0.f);
-    for (int ks = 0; ks < Lp / 16; ++ks) {
-        wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> a;
+    const int nks = Lp / 16;
+    for (int ks = 0; ks < nks; ks += 2) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> a0, a1;
         wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> b0, b1;
-        wmma::load_matrix_sync(a, Ps + wr * 16 * ldP + ks * 16, ldP);
-        wmma::load_matrix_sync(b0, Ys + ks * 16 * AT_LD + (2 * wh) * 16, AT_LD);
-        wmma::load_matrix_sync(b1, Ys + ks * 16 * AT_LD + (2 * wh + 1) * 16, AT_LD);
-        wmma::mma_sync(c0, a, b0, c0);
-        wmma::mma_sync(c1, a, b1, c1);
+        wmma::load_matrix_sync(a0, Ps + wr * 16 * ldP + ks * 16, ldP);
+        wmma::load_matrix_sync(b0, Ys + ks * 16 * AT_LD + wq * 16, AT_LD);
+        if (ks + 1 < nks) {
+            wmma::load_matrix_sync(a1, Ps + wr * 16 * ldP + (ks + 1) * 16, ldP);
+            wmma::load_matrix_sync(b1, Ys + (ks + 1) * 16 * AT_LD + wq * 16, AT_LD);
+        }
+        wmma::mma_sync(c0, a0, b0, c0);
+        if (ks + 1 < nks) wmma::mma_sync(c1, a1, b1, c1);
     }
-    wmma::store_matrix_sync(out + wr * 16 * AT_OLD + (2 * wh) * 16, c0, AT_OLD, wmma::mem_row_major);
-    wmma::store_matrix_sync(out + wr * 16 * AT_OLD + (2 * wh + 1) * 16, c1, AT_OLD, wmma::mem_row_major);
+#pragma unroll
+    for (int i = 0; i < c0.num_elements; ++i) c0.x[i] += c1.x[i];
+    wmma::store_matrix_sync(out + wr * 16 * AT_OLD + wq * 16, c0, AT_OLD, wmma::mem_row_major);
 }
 
 // (48 x 64) fp32 staging tile -> bf16 rows of a (T, row_stride) matrix, optionally scaled per row
@@ -128,7 +138,7 @@ attn_fwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, bf16 *_
     bf16 *Qs = reinterpret_cast<bf16 *>(smem + lay.q), *Pb = reinterpret_cast<bf16 *>(smem + lay.p);
     float *Sf = reinterpret_cast<float *>(smem + lay.s), *rowinv = reinterpret_cast<float *>(smem + lay.rowinv);
     const int t0 = blockIdx.x * AT_QT, h = blockIdx.y, b = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp % 3, wh = warp / 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp % 3, wq = warp / 3;
     const int ldS = Lp + 4, ldP = Lp + 8;
     const size_t rs = (size_t)3 * C;
     const bf16 *base = qkv + (size_t)b * L * rs + h * AT_D;
@@ -137,11 +147,12 @@ attn_fwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, bf16 *_
     at_load_rows(Ks, base + C, rs, 0, L, Lp);
     at_load_rows(Vs, base + 2 * C, rs, 0, L, Lp);
     at_load_rows(Qs, base, rs, t0, n_q, AT_QT);
+    at_async_wait();
     __syncthreads();
-    at_gemm_xyT(Sf, ldS, Qs, 0, Ks, Lp, wr, wh);
+    at_gemm_xyT(Sf, ldS, Qs, 0, Ks, Lp, wr, wq);
     __syncthreads();
-    // softmax over the L valid keys; rows warp*8 .. warp*8+7
-    for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+    // softmax over the L valid keys; 4 rows per warp
+    for (int r = warp * 4; r < warp * 4 + 4; ++r) {
         const float *srow = Sf + r * ldS;
         float m = -INFINITY;
         for (int c = lane; c < L; c += 32) m = fmaxf(m, srow[c] * scale);
@@ -160,13 +171,13 @@ attn_fwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, bf16 *_
         }
     }
     __syncthreads();
-    at_gemm_py(Sf, Pb, ldP, Vs, Lp, wr, wh);          // S is dead: its region stages the (48 x 64) output
+    at_gemm_py(Sf, Pb, ldP, Vs, Lp, wr, wq);          // S is dead: its region stages the (48 x 64) output
     __syncthreads();
     at_store_rows(o + (size_t)b * L * C + h * AT_D, C, t0, n_q, Sf, rowinv);
 }
 
 struct AttnSmemBwd {
-    size_t q, k, v, dO, lse, delta, s, dp, p, ds, total;
+    size_t q, k, v, dO, lse, delta, s, dp, p, ds, total;     // the forward output O is staged in the (not yet used) P/dS region
     __host__ __device__ AttnSmemBwd(int Lp, int Lr) {
         size_t o = 0;
         q = o; o = at_align128(o + (size_t)Lr * AT_LD * 2);
@@ -195,7 +206,7 @@ attn_bwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const b
     float *Sf = reinterpret_cast<float *>(smem + lay.s), *dPf = reinterpret_cast<float *>(smem + lay.dp);
     bf16 *Pb = reinterpret_cast<bf16 *>(smem + lay.p), *dSb = reinterpret_cast<bf16 *>(smem + lay.ds);
     const int t0 = blockIdx.x * AT_QT, h = blockIdx.y, b = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp % 3, wh = warp / 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wr = warp % 3, wq = warp / 3;
     const int ldS = Lp + 4, ldP = Lp + 8;
     const size_t rs = (size_t)3 * C;
     const bf16 *base = qkv + (size_t)b * L * rs + h * AT_D;
@@ -208,24 +219,43 @@ attn_bwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const b
     at_load_rows(Vs, base + 2 * C, rs, 0, L, Lr);
     at_load_rows(dOs, dobase, C, 0, L, Lr);
     for (int r = threadIdx.x; r < Lp; r += AT_THREADS) lse_s[r] = r < L ? lse[((size_t)b * H + h) * L + r] : 0.f;
-    __syncthreads();
-    // delta_i = sum_d dO[i][d] * O[i][d]
-    for (int r = warp; r < Lp; r += AT_THREADS / 32) {
-        float v = 0.f;
-        if (r < L) {
-            const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162 *>(obase + (size_t)r * C + 2 * lane);
-            const __nv_bfloat162 dv = *reinterpret_cast<const __nv_bfloat162 *>(dOs + r * AT_LD + 2 * lane);
-            const float2 of = __bfloat1622float2(ov), df = __bfloat1622float2(dv);
-            v = of.x * df.x + of.y * df.y;
+    // delta_i = sum_d dO[i][d] * O[i][d]: 8 threads per row (one 16-byte chunk each), O straight from global
+    {
+        uint4 ov[(AT_MAX_L * 8 + AT_THREADS - 1) / AT_THREADS];
+#pragma unroll
+        for (int j = 0; j < (AT_MAX_L * 8 + AT_THREADS - 1) / AT_THREADS; ++j) {
+            const int i = threadIdx.x + j * AT_THREADS, r = i >> 3, ch = i & 7;
+            ov[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < Lp * 8 && r < L) ov[j] = *reinterpret_cast<const uint4 *>(obase + (size_t)r * C + ch * 8);
         }
-        v = warp_sum(v);
-        if (lane == 0) delta_s[r] = v;
+        at_async_wait();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < (AT_MAX_L * 8 + AT_THREADS - 1) / AT_THREADS; ++j) {
+            const int i = threadIdx.x + j * AT_THREADS, r = i >> 3, ch = i & 7;
+            float v = 0.f;
+            if (i < Lp * 8) {
+                const uint4 dv = *reinterpret_cast<const uint4 *>(dOs + r * AT_LD + ch * 8);
+                const __nv_bfloat162 *oh = reinterpret_cast<const __nv_bfloat162 *>(&ov[j]);
+                const __nv_bfloat162 *dh = reinterpret_cast<const __nv_bfloat162 *>(&dv);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 of = __bfloat1622float2(oh[k]), df = __bfloat1622float2(dh[k]);
+                    v = fmaf(of.x, df.x, fmaf(of.y, df.y, v));
+                }
+            }
+            // (Lp*8 is a multiple of 32 and AT_THREADS a multiple of 8: the 8 lanes of a row are in one warp, all active)
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if (i < Lp * 8 && ch == 0) delta_s[r] = v;
+        }
     }
     __syncthreads();
 
     // ---------------- role A: queries of this tile -> dQ
-    at_gemm_xyT(Sf, ldS, Qs, t0, Ks, Lp, wr, wh);
-    at_gemm_xyT(dPf, ldS, dOs, t0, Vs, Lp, wr, wh);
+    at_gemm_xyT(Sf, ldS, Qs, t0, Ks, Lp, wr, wq);
+    at_gemm_xyT(dPf, ldS, dOs, t0, Vs, Lp, wr, wq);
     __syncthreads();
     for (int i = threadIdx.x; i < AT_QT * Lp; i += AT_THREADS) {
         const int r = i / Lp, c = i - r * Lp;
@@ -238,14 +268,14 @@ attn_bwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const b
         dSb[r * ldP + c] = __float2bfloat16_rn(ds);
     }
     __syncthreads();
-    at_gemm_py(Sf, dSb, ldP, Ks, Lp, wr, wh);
+    at_gemm_py(Sf, dSb, ldP, Ks, Lp, wr, wq);
     __syncthreads();
     at_store_rows(dbase, rs, t0, n_t, Sf, nullptr);
     __syncthreads();
 
     // ---------------- role B: keys of this tile -> dK, dV  (transposed problem: rows = keys, columns = queries)
-    at_gemm_xyT(Sf, ldS, Ks, t0, Qs, Lp, wr, wh);
-    at_gemm_xyT(dPf, ldS, Vs, t0, dOs, Lp, wr, wh);
+    at_gemm_xyT(Sf, ldS, Ks, t0, Qs, Lp, wr, wq);
+    at_gemm_xyT(dPf, ldS, Vs, t0, dOs, Lp, wr, wq);
     __syncthreads();
     for (int i = threadIdx.x; i < AT_QT * Lp; i += AT_THREADS) {
         const int r = i / Lp, c = i - r * Lp;
@@ -258,8 +288,8 @@ attn_bwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const b
         dSb[r * ldP + c] = __float2bfloat16_rn(ds);
     }
     __syncthreads();
-    at_gemm_py(Sf, Pb, ldP, dOs, Lp, wr, wh);          // dV_t = P^T dO
-    at_gemm_py(dPf, dSb, ldP, Qs, Lp, wr, wh);         // dK_t = dS^T Q
+    at_gemm_py(Sf, Pb, ldP, dOs, Lp, wr, wq);          // dV_t = P^T dO
+    at_gemm_py(dPf, dSb, ldP, Qs, Lp, wr, wq);         // dK_t = dS^T Q
     __syncthreads();
     at_store_rows(dbase + 2 * C, rs, t0, n_t, Sf, nullptr);
     at_store_rows(dbase + C, rs, t0, n_t, dPf, nullptr);

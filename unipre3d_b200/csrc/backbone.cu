@@ -423,8 +423,7 @@ template <typename AT>
 static int launch_ln_bwd(int NV, int T, int L, const void *dy, const float *xs, const float *mean, const float *rstd,
                          const float *gamma, const float *g_res, const float *scale, float *dx, float *dpos, void *dscaled,
                          float *dgamma, float *dbeta, float *dbias, cudaStream_t st) {
-    // two rows per warp: the column-sum atomics (one per column, array and CTA) bound this kernel, not its 6 MB of data
-    const int grid = min(div_up(T, 2 * LN_WARPS), UP3D_NUM_SMS);
+    const int grid = min(div_up(T, LN_WARPS), UP3D_NUM_SMS);     // one row per warp (measured faster than two)
 #define LN_BWD_CASE(N)                                                                                              \
     case N:                                                                                                         \
         ln_bwd_kernel<AT, N><<<grid, LN_WARPS * 32, 0, st>>>(T, L, (const AT *)dy, xs, mean, rstd, gamma, g_res, scale, dx, \
