@@ -34,6 +34,7 @@ constexpr int AT_OLD = 68;        // fp32 row stride of the (48, 64) output stag
 constexpr int AT_THREADS = 384;   // 12 warps: (row strip wr = warp % 3, column quarter wq = warp / 3); the kernels are
                                   // latency-bound chains of fragment loads and MMAs, so warps per SM matter more than tile reuse
 constexpr int AT_MAX_L = 192;
+constexpr int AT_NP = AT_MAX_L / 64;   // column pairs per lane in the row-wise passes (c = 2*lane + 64*j)
 
 __host__ __device__ inline int at_round16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline size_t at_align128(size_t x) { return (x + 127) & ~(size_t)127; }
@@ -151,18 +152,36 @@ attn_fwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, bf16 *_
     __syncthreads();
     at_gemm_xyT(Sf, ldS, Qs, 0, Ks, Lp, wr, wq);
     __syncthreads();
-    // softmax over the L valid keys; 4 rows per warp
-    for (int r = warp * 4; r < warp * 4 + 4; ++r) {
+    // softmax over the L valid keys; 4 rows per warp, a lane owns the column pairs c = 2*lane + 64*j (kept in
+    // registers between the max and the exp pass: one shared-memory read, one packed bf16x2 write per pair)
+#pragma unroll
+    for (int rr = 0; rr < AT_QT / (AT_THREADS / 32); ++rr) {
+        const int r = warp * (AT_QT / (AT_THREADS / 32)) + rr;
         const float *srow = Sf + r * ldS;
+        float2 v[AT_NP];
         float m = -INFINITY;
-        for (int c = lane; c < L; c += 32) m = fmaxf(m, srow[c] * scale);
+#pragma unroll
+        for (int j = 0; j < AT_NP; ++j) {
+            const int c = 2 * lane + 64 * j;
+            v[j] = make_float2(-INFINITY, -INFINITY);
+            if (c < Lp) {
+                const float2 t = *reinterpret_cast<const float2 *>(srow + c);
+                if (c < L) v[j].x = t.x * scale;
+                if (c + 1 < L) v[j].y = t.y * scale;
+            }
+            m = fmaxf(m, fmaxf(v[j].x, v[j].y));
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
         float sum = 0.f;
-        for (int c = lane; c < Lp; c += 32) {
-            float e = 0.f;
-            if (c < L) { e = __expf(srow[c] * scale - m); sum += e; }
-            Pb[r * ldP + c] = __float2bfloat16_rn(e);
+#pragma unroll
+        for (int j = 0; j < AT_NP; ++j) {
+            const int c = 2 * lane + 64 * j;
+            if (c < Lp) {
+                const float e0 = __expf(v[j].x - m), e1 = __expf(v[j].y - m);      // exp(-inf) = 0 for masked keys
+                sum += e0 + e1;
+                *reinterpret_cast<__nv_bfloat162 *>(Pb + r * ldP + c) = __floats2bfloat162_rn(e0, e1);
+            }
         }
         sum = warp_sum(sum);
         if (lane == 0) {
@@ -257,15 +276,22 @@ attn_bwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const b
     at_gemm_xyT(Sf, ldS, Qs, t0, Ks, Lp, wr, wq);
     at_gemm_xyT(dPf, ldS, dOs, t0, Vs, Lp, wr, wq);
     __syncthreads();
-    for (int i = threadIdx.x; i < AT_QT * Lp; i += AT_THREADS) {
-        const int r = i / Lp, c = i - r * Lp;
-        float ds = 0.f;
-        if (r < n_t && c < L) {
-            const int qi = t0 + r;
-            const float p = __expf(Sf[r * ldS + c] * scale - lse_s[qi]);
-            ds = p * (dPf[r * ldS + c] - delta_s[qi]) * scale;
+#pragma unroll
+    for (int rr = 0; rr < AT_QT / (AT_THREADS / 32); ++rr) {
+        const int r = warp * (AT_QT / (AT_THREADS / 32)) + rr;
+        const bool row_ok = r < n_t;
+        const float l = row_ok ? lse_s[t0 + r] : 0.f, dl = row_ok ? delta_s[t0 + r] : 0.f;
+#pragma unroll
+        for (int j = 0; j < AT_NP; ++j) {
+            const int c = 2 * lane + 64 * j;
+            if (c < Lp) {
+                const float2 s2 = *reinterpret_cast<const float2 *>(Sf + r * ldS + c);
+                const float2 d2 = *reinterpret_cast<const float2 *>(dPf + r * ldS + c);
+                const float x = (row_ok && c < L) ? __expf(s2.x * scale - l) * (d2.x - dl) * scale : 0.f;
+                const float y = (row_ok && c + 1 < L) ? __expf(s2.y * scale - l) * (d2.y - dl) * scale : 0.f;
+                *reinterpret_cast<__nv_bfloat162 *>(dSb + r * ldP + c) = __floats2bfloat162_rn(x, y);
+            }
         }
-        dSb[r * ldP + c] = __float2bfloat16_rn(ds);
     }
     __syncthreads();
     at_gemm_py(Sf, dSb, ldP, Ks, Lp, wr, wq);
@@ -277,15 +303,25 @@ attn_bwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const b
     at_gemm_xyT(Sf, ldS, Ks, t0, Qs, Lp, wr, wq);
     at_gemm_xyT(dPf, ldS, Vs, t0, dOs, Lp, wr, wq);
     __syncthreads();
-    for (int i = threadIdx.x; i < AT_QT * Lp; i += AT_THREADS) {
-        const int r = i / Lp, c = i - r * Lp;
-        float p = 0.f, ds = 0.f;
-        if (r < n_t && c < L) {
-            p = __expf(Sf[r * ldS + c] * scale - lse_s[c]);
-            ds = p * (dPf[r * ldS + c] - delta_s[c]) * scale;
+#pragma unroll
+    for (int rr = 0; rr < AT_QT / (AT_THREADS / 32); ++rr) {
+        const int r = warp * (AT_QT / (AT_THREADS / 32)) + rr;
+        const bool row_ok = r < n_t;
+#pragma unroll
+        for (int j = 0; j < AT_NP; ++j) {
+            const int c = 2 * lane + 64 * j;
+            if (c < Lp) {
+                const float2 s2 = *reinterpret_cast<const float2 *>(Sf + r * ldS + c);
+                const float2 d2 = *reinterpret_cast<const float2 *>(dPf + r * ldS + c);
+                const float2 l2 = *reinterpret_cast<const float2 *>(lse_s + c);
+                const float2 dl2 = *reinterpret_cast<const float2 *>(delta_s + c);
+                const float p0 = (row_ok && c < L) ? __expf(s2.x * scale - l2.x) : 0.f;
+                const float p1 = (row_ok && c + 1 < L) ? __expf(s2.y * scale - l2.y) : 0.f;
+                *reinterpret_cast<__nv_bfloat162 *>(Pb + r * ldP + c) = __floats2bfloat162_rn(p0, p1);
+                *reinterpret_cast<__nv_bfloat162 *>(dSb + r * ldP + c) =
+                    __floats2bfloat162_rn(p0 * (d2.x - dl2.x) * scale, p1 * (d2.y - dl2.y) * scale);
+            }
         }
-        Pb[r * ldP + c] = __float2bfloat16_rn(p);
-        dSb[r * ldP + c] = __float2bfloat16_rn(ds);
     }
     __syncthreads();
     at_gemm_py(Sf, Pb, ldP, dOs, Lp, wr, wq);          // dV_t = P^T dO
