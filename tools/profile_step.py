@@ -24,4 +24,4 @@ else:
         for _ in range(3):
             tr.train_iteration(data)
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=int(os.environ.get('ROWS', '45')), max_name_column_width=70))
