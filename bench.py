@@ -93,12 +93,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def ncu_traffic(kernel_substr: str):
+def ncu_traffic(kernel_substr: str, pattern: str = "*_P128_ncu_raw.csv"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_substr` from the newest committed
-    `ncu --set full` capture of the transformer-config raster kernels (profiles/*_P128_ncu_raw.csv); None if absent."""
+    `ncu --set full` capture matching profiles/<pattern> (default: the transformer-config raster kernels); None if
+    absent."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_P128_ncu_raw.csv")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
     if not files:
         return None, None
     try:
@@ -282,7 +283,9 @@ def ours(args):
     autocast = None if args.fp32 else torch.bfloat16
     trainer = Trainer(cfg, device=device, use_cuda_graph=use_graph, autocast_dtype=autocast)
     n_batches = 4
-    batches = [synthetic.make_batch(cfg, OBJECTS_PER_GPU, N_POINTS, seed=1000 * rank + i, pin=True) for i in range(n_batches)]
+    image_dtype = "float32" if args.float_images else "uint8"
+    batches = [synthetic.make_batch(cfg, OBJECTS_PER_GPU, N_POINTS, seed=1000 * rank + i, pin=True, image_dtype=image_dtype)
+               for i in range(n_batches)]
     h2d = synthetic.batch_nbytes(batches[0])
     views_per_step = OBJECTS_PER_GPU * int(cfg.opt.imgs_per_obj) * n_gpus
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)     # > 126 MB L2
@@ -353,6 +356,22 @@ def ours(args):
         extra.update(raster_roofline(trainer, resident, cfg, max(3, min(args.steps, 10)), peaks, peak_kind))
     except Exception as e:  # never lose the headline because a side measurement failed
         extra["roofline_error"] = repr(e)
+    try:
+        # the optimizer pass: the step's largest HBM-bound kernel (one read-modify-write over param/grad/moments)
+        trainer._forward_backward(resident)
+        trainer._allreduce_grads()
+        sq_ms, ap_ms, ap_bytes = trainer.model_manager.optimizer.time_passes(5)
+        trainer.model_manager.optimizer.zero_grad(set_to_none=True)
+        tr_adam, tr_src = ncu_traffic("adamw_kernel", "*_step_ncu_raw.csv")
+        extra["roofline_hbm_kernel"] = {
+            "bound": "hbm", "kernel": "up3d::adamw_kernel", "achieved": ap_bytes / (ap_ms * 1e-3) / 1e9,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ap_bytes / (ap_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "traffic": tr_adam, "traffic_source": tr_src, "peak_source": peak_kind,
+            "algorithmic_bytes_per_launch": ap_bytes, "launch_ms": ap_ms,
+            "note": "28 B per parameter (read param/grad/exp_avg/exp_avg_sq, write param/exp_avg/exp_avg_sq) + 2 B per "
+                    "bf16-shadowed parameter; grad_sumsq_kernel (4 B/param) takes %.4f ms" % sq_ms}
+    except Exception as e:
+        extra["roofline_hbm_kernel_error"] = repr(e)
     if rank == 0:
         try:
             extra["raster_only"] = raster_only_headline(device, 5, peaks)
@@ -377,6 +396,8 @@ def ours(args):
                                        "256x256, 128 Gaussians/object, SH degree 1 (BASELINE.json configs[1])",
                            "objects_per_gpu": OBJECTS_PER_GPU, "views_per_step": views_per_step, "parallelism": f"dp{n_gpus}",
                            "cuda_graph": bool(use_graph),
+                           "host_images": ("float32 (divided by 255 on the host, as the reference loader)" if args.float_images
+                                           else "uint8 as decoded from the dataset's PNGs; /255 on the device"),
                            "l2": "256 MiB buffer written between timed iterations (L2 flush), per-step CUDA-event pairs"},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "views/s", "ms_per_step": ms_e2e / args.steps,
@@ -404,6 +425,7 @@ def main():
     ap.add_argument("--fp32", action="store_true", help="keep the backbone GEMMs in fp32 (reference precision)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--float-images", action="store_true", help="host batches carry float32 images (4x the H2D bytes)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -134,3 +134,23 @@ def test_shadow_bf16_weights_equal_autocast():
     assert abs(la[0] - lb[0]) <= 1e-3 * abs(la[0])              # same forward (bf16 rounding of the same operands)
     assert abs(la[-1] - lb[-1]) <= 2e-2 * abs(la[-1])
     assert lb[-1] < lb[0]
+
+
+def test_uint8_host_images_equal_float_images():
+    """8-bit host images divided by 255 on the device give the same step as the float images the reference's loader
+    produces on the host (a quarter of the host->device bytes)."""
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.trainer import Trainer, _to_device
+    cfg = _cfg(res=64, bs=2)
+    b8 = synthetic.make_batch(cfg, 2, 1024, seed=9, image_dtype="uint8")
+    assert b8["gt_images"].dtype == torch.uint8 and synthetic.batch_nbytes(b8) < 0.3 * synthetic.batch_nbytes(
+        synthetic.make_batch(cfg, 2, 1024, seed=9))
+    bf = dict(b8)
+    bf["gt_images"] = b8["gt_images"].float() / 255.0
+    losses = []
+    for batch in (b8, bf):
+        torch.manual_seed(0)
+        tr = Trainer(cfg, use_cuda_graph=False)
+        torch.manual_seed(1)
+        losses.append(float(tr._forward_backward(_to_device(batch, tr.device))))
+    assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[1])

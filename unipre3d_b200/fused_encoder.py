@@ -106,6 +106,35 @@ def _wgrad(dy, x):
     return torch.mm(dy.t(), x, out_dtype=torch.float32)
 
 
+_SIDE_STREAMS = {}
+
+
+class SideStream:
+    """Runs work that is OFF the backward critical path (the weight-gradient GEMMs: nothing downstream in the backward
+    needs them) on a second stream, so their launch latency and tails overlap the dX chain -- at 1032 tokens every GEMM of
+    this stack is latency-, not throughput-bound.  Fork/join with stream events (captured as parallel graph branches);
+    inputs handed to the side stream are kept alive until the join so the allocator cannot recycle them early."""
+
+    def __init__(self, device):
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device())
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        self.side = _SIDE_STREAMS[key]
+        self.keep = []
+
+    def run(self, fn, *tensors):
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            out = fn(*tensors)
+        self.keep.extend(tensors)
+        return out
+
+    def join(self):
+        self.main.wait_stream(self.side)
+        self.keep.clear()
+
+
 class _Meta:
     """Non-tensor arguments of the stack (one object so that autograd sees a single opaque input)."""
 
@@ -185,6 +214,7 @@ class EncoderStackFn(torch.autograd.Function):
 
             # slots: 0 n1w, 1 n1b, 2 bproj, 3 n2w, 4 n2b, 5 b2, 6.. b1
             s2_last = masks[2 * depth - 1] if masks is not None else None
+            side = SideStream(dev)
             dd = scale_cast_colsum(g, s2_last, L, act, sm(depth - 1, 5))
             for i in range(depth - 1, -1, -1):
                 xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h, qkv, lse = sv[SAVED_PER_BLOCK * i:SAVED_PER_BLOCK * (i + 1)]
@@ -194,14 +224,14 @@ class EncoderStackFn(torch.autograd.Function):
                 s2_prev = masks[2 * i - 1] if (masks is not None and i > 0) else None
                 # ---- MLP branch
                 dh = dd @ w2
-                gw2 = _wgrad(dd, h)
+                gw2 = side.run(_wgrad, dd, h)
                 dpre = gelu_bwd(dh, pre, sm(i, 6, Hd))
                 dy2 = dpre @ w1
-                gw1 = _wgrad(dpre, y2)
+                gw1 = side.run(_wgrad, dpre, y2)
                 dx2, da = ln_bwd(dy2, x2, mu2, rs2, n2w, g, s1, L, None, True, sm(i, 3), sm(i, 4), sm(i, 2))
                 # ---- attention branch
                 do = da @ wproj
-                gwproj = _wgrad(da, o)
+                gwproj = side.run(_wgrad, da, o)
                 if ctx.own_attn:
                     dqkv = attn_bwd(qkv, o, lse, do, B, L, H, D, meta.scale)
                 else:
@@ -209,7 +239,7 @@ class EncoderStackFn(torch.autograd.Function):
                     (dqkv,) = torch.autograd.grad(o_l, qkv_l, do)
                     dqkv = dqkv.contiguous()
                 dy1 = dqkv @ wqkv
-                gwqkv = _wgrad(dqkv, y1)
+                gwqkv = side.run(_wgrad, dqkv, y1)
                 g, dd = ln_bwd(dy1, xs, mu1, rs1, n1w, dx2, s2_prev, L, dpos, i > 0, sm(i, 0), sm(i, 1),
                                sm(i - 1, 5) if i > 0 else None)
                 base = i * PARAMS_PER_BLOCK
@@ -218,6 +248,7 @@ class EncoderStackFn(torch.autograd.Function):
                 grads[base + 5], grads[base + 6] = sm(i, 3), sm(i, 4)
                 grads[base + 7], grads[base + 8] = gw1, sm(i, 6, Hd)
                 grads[base + 9], grads[base + 10] = gw2, sm(i, 5)
+            side.join()
             ctx.attn_nodes = None
         gx = g.view(B, L, C) if ctx.needs_input_grad[0] else None
         gp = dpos.view(B, L, C) if ctx.needs_input_grad[1] else None

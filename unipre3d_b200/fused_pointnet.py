@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from ._lib import check, ptr, require_cuda, stream_ptr
-from .fused_encoder import _flag, _wgrad
+from .fused_encoder import SideStream, _flag, _wgrad
 
 _NUM_SMS = 148
 
@@ -145,8 +145,9 @@ class MiniPointNetFn(torch.autograd.Function):
             # ---- layer 4
             dz4 = torch.empty((R, C4), dtype=act, device=dev)
             check(L.up3d_group_max_scatter(fl, Gt, K, C4, ptr(dt), ptr(arg4), ptr(dz4), stream_ptr()), 1)
+            side = SideStream(dev)                      # weight-gradient GEMMs overlap the dX chain
             dy3 = dz4 @ W4c
-            gW4 = _wgrad(dz4, y3)
+            gW4 = side.run(_wgrad, dz4, y3)
             # ---- BN2 + ReLU backward (+ group sums for the global half)
             n2 = (Gt + gpc - 1) // gpc
             part = torch.empty((n2, 2, C3), dtype=torch.float32, device=dev)
@@ -161,13 +162,13 @@ class MiniPointNetFn(torch.autograd.Function):
             W3g, W3l = W3c[:, :C2], W3c[:, C2:]
             dfl = dz3 @ W3l
             dfg = dgp @ W3g
-            gW3 = torch.cat([_wgrad(dgp, fg), _wgrad(dz3, f)], dim=1)
+            gW3 = side.run(lambda a, b, c, d: torch.cat([_wgrad(a, b), _wgrad(c, d)], dim=1), dgp, fg, dz3, f)
             # ---- group max backward + layer 2
             gb2 = torch.zeros(C2, dtype=torch.float32, device=dev)
             df = torch.empty((R, C2), dtype=act, device=dev)
             check(L.up3d_group_combine(fl, Gt, K, C2, gpc, ptr(dfl), ptr(dfg), ptr(arg2), ptr(df), ptr(gb2), stream_ptr()), 1)
             dy1 = df @ W2c
-            gW2 = _wgrad(df, y1)
+            gW2 = side.run(_wgrad, df, y1)
             # ---- BN1 + ReLU + layer 1 backward
             n1 = min((R + 127) // 128, 2 * _NUM_SMS)
             part1 = torch.empty((n1, 2, C1), dtype=torch.float32, device=dev)
@@ -179,6 +180,7 @@ class MiniPointNetFn(torch.autograd.Function):
             check(L.up3d_pn_conv1_bwd(fl, 1, R, GK, ptr(nb), ptr(w1), ptr(b1), ptr(stats1), ptr(dy1), ptr(sums1g),
                                       float(R * wd1), None, n1, ptr(gW1), ptr(gb1), stream_ptr()), 1)
             gb3 = torch.zeros(C3, dtype=torch.float32, device=dev)       # bias in front of a train-mode BatchNorm
+            side.join()
         return (None, None, gW1.view(C1, 3, 1), gb1, sums1[1], sums1[0], gW2.view(C2, C1, 1), gb2, gW3.view(C3, 2 * C2, 1),
                 gb3, sums2[1], sums2[0], gW4.view(C4, C3, 1), gb4)
 

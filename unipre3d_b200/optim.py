@@ -162,6 +162,35 @@ class FusedClipAdamW(torch.optim.AdamW):
                   launches=2)
         return None
 
+    @torch.no_grad()
+    def time_passes(self, reps: int = 5):
+        """CUDA-event timing of the two launches on the current stream (bench.py roofline): -> (sumsq_ms, apply_ms,
+        algorithmic bytes of the apply pass).  Every repetition is a REAL optimizer step on the current gradients."""
+        if not self._built:
+            self._build()
+        self._upload_grad_ptrs()
+        g0, L = self.param_groups[0], _lib.lib
+        head = (len(self._params), self._n_chunks, ptr(self._chunk_tensor), ptr(self._chunk_start), ptr(self._numel))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_sq = t_ap = 0.0
+        with torch.cuda.device(self._dev):
+            for _ in range(reps):
+                ev[0].record()
+                check(L.up3d_grad_sumsq(*head, ptr(self._g_ptrs), ptr(self._state), stream_ptr()), launches=1)
+                ev[1].record()
+                check(L.up3d_adamw_apply(*head, ptr(self._p_ptrs), ptr(self._g_ptrs), ptr(self._m_ptrs), ptr(self._v_ptrs),
+                                         ptr(self._s_ptrs), ptr(self._group), ptr(self._lrs), float(g0["betas"][0]),
+                                         float(g0["betas"][1]), float(g0["eps"]), float(g0["weight_decay"]), self.max_norm,
+                                         ptr(self._state), stream_ptr()), launches=1)
+                ev[2].record()
+                torch.cuda.synchronize()
+                t_sq += ev[0].elapsed_time(ev[1])
+                t_ap += ev[1].elapsed_time(ev[2])
+        n = sum(p.numel() for p in self._params)
+        n_sh = sum(p.numel() for p in self._params if id(p) in self._shadows)
+        # read param, grad, exp_avg, exp_avg_sq (16 B) + write param, exp_avg, exp_avg_sq (12 B) [+ 2 B bf16 shadow]
+        return t_sq / reps, t_ap / reps, 28 * n + 2 * n_sh
+
     # device scalars of the most recent step (reading them is a D2H sync: diagnostics / tests only)
     def last_total_norm(self) -> float:
         return float(self._state[3])

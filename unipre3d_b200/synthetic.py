@@ -41,7 +41,13 @@ def make_cloud(n_points: int, rng: np.random.Generator, in_channels: int = 3) ->
     return p.astype(np.float32)
 
 
-def make_batch(cfg, batch_size: int, n_points: int, seed: int = 0, pin: bool = False) -> Dict[str, torch.Tensor]:
+def make_batch(cfg, batch_size: int, n_points: int, seed: int = 0, pin: bool = False,
+               image_dtype: str = "float32") -> Dict[str, torch.Tensor]:
+    """image_dtype "float32": the dict the reference loader emits (images already divided by 255 on the host,
+    shapenet.py:640-661).  "uint8": the same images as decoded from the dataset's 8-bit PNGs -- a quarter of the
+    host->device bytes; Trainer divides by 255 on the device."""
+    if image_dtype not in ("float32", "uint8"):
+        raise ValueError(f"image_dtype {image_dtype!r}")
     rng = np.random.default_rng(seed)
     V = int(cfg.data.input_images) + int(cfg.opt.imgs_per_obj)
     R = int(cfg.data.training_resolution)
@@ -58,8 +64,12 @@ def make_batch(cfg, batch_size: int, n_points: int, seed: int = 0, pin: bool = F
         clouds.append(make_cloud(n_points, rng, int(cfg.model.in_channels)))
         cx, cy, rad = rng.uniform(0.35 * R, 0.65 * R), rng.uniform(0.35 * R, 0.65 * R), rng.uniform(0.2 * R, 0.4 * R)
         disc = ((xx - cx) ** 2 + (yy - cy) ** 2) <= rad ** 2
-        img = rng.uniform(0, 1, (V, 3, R, R)).astype(np.float32)
-        gts.append(np.where(disc[None, None], img, np.float32(bgc)))
+        if image_dtype == "uint8":
+            img = rng.integers(0, 256, (V, 3, R, R), dtype=np.uint8)
+            gts.append(np.where(disc[None, None], img, np.uint8(255 * bgc)))
+        else:
+            img = rng.uniform(0, 1, (V, 3, R, R)).astype(np.float32)
+            gts.append(np.where(disc[None, None], img, np.float32(bgc)))
     batch = {k: torch.stack(v).float() for k, v in out.items()}
     batch["gt_images"] = torch.from_numpy(np.stack(gts))
     batch["point_cloud"] = {"pos": torch.from_numpy(np.stack(clouds))}

@@ -221,8 +221,18 @@ class Trainer:
         gt = data["gt_images"][:, sl]
         return rendered.reshape(-1, *rendered.shape[2:]), gt.reshape(-1, *gt.shape[2:])
 
+    @staticmethod
+    def _decode_images(data):
+        """8-bit images (as decoded from the dataset's PNGs) are divided by 255 on the device: the host->device copy
+        moves a quarter of the bytes of the float images the reference's loader produces on the host."""
+        if data["gt_images"].dtype == torch.uint8:
+            data = dict(data)
+            data["gt_images"] = data["gt_images"].to(torch.float32).div_(255.0)
+        return data
+
     def _forward_backward(self, data) -> torch.Tensor:
         mm = self.model_manager
+        data = self._decode_images(data)
         model_inputs = prepare_model_inputs(data, self.cfg, self.bs_per_gpu, self.device)
         mm.forward_model.train()
         if self.autocast_dtype is not None:
