@@ -281,14 +281,15 @@ UP3D_API int up3d_pn_conv1_stats(int R, int GK, const float *nb, const float *W1
 UP3D_API int up3d_pn_conv1_bn_relu(int act_bf16, int R, int GK, const float *nb, const float *W1, const float *b1,
                                    const float *stats, void *y1, up3d_stream_t stream);
 /* backward of the same three ops from dy1 (R,128).  pass 0: partials (n_partials,2,128) of sum dy, sum dy*xhat (dy masked
- * by the ReLU); pass 1 (sums (2,128) = reduced pass-0 partials): gW1 (128,3) += dz x^T, gb1 (128) += dz (atomic
- * accumulate; zero them first), dz = a (dy - mean(dy) - xhat mean(dy xhat)), means = sums / count (count = the number of
+ * by the ReLU); pass 1 (sums (2,128) = reduced pass-0 partials): partials (n_partials,2,256) with row 0 =
+ * [gW1[:,0] | gW1[:,1]], row 1 = [gW1[:,2] | gb1] (reduce with up3d_bn_reduce_sums; gW1/gb1 arguments are unused),
+ * dz = a (dy - mean(dy) - xhat mean(dy xhat)), means = sums / count (count = the number of
  * rows the batch statistics were taken over: R, or R * world under SyncBatchNorm). */
 UP3D_API int up3d_pn_conv1_bwd(int act_bf16, int pass, int R, int GK, const float *nb, const float *W1, const float *b1,
                                const float *stats, const void *dy1, const float *sums, double count, float *partials,
                                int n_partials, float *gW1, float *gb1, up3d_stream_t stream);
-/* backward sums: partials (n_partials,2,C) -> sums (2,C), fp64 accumulation. */
-UP3D_API int up3d_bn_reduce_sums(int n_partials, int C, const float *partials, float *sums, up3d_stream_t stream);
+/* partial sums (n_partials, n_rows, C) -> sums (n_rows, C), n_rows = 1 or 2, fp64 accumulation. */
+UP3D_API int up3d_bn_reduce_sums(int n_partials, int n_rows, int C, const float *partials, float *sums, up3d_stream_t stream);
 /* forward statistics: partials (n_partials,3,C) = [shift, sum (z-shift), sum (z-shift)^2], partial p covering
  * min(rows_per_partial, total_rows - p*rows_per_partial) rows, merged pairwise in fp64 into the batch mean / M2 ->
  * triple_out (3,C) = [mean, 0, M2] (same format: a second-level merge across ranks for SyncBatchNorm; may be NULL)
@@ -315,12 +316,39 @@ UP3D_API int up3d_gbn_bwd_apply(int act_bf16, int Gt, int K, int C, int gpc, con
                                 void *dgroup, up3d_stream_t stream);
 /* per-group max-pool over the K rows (torch.max(dim), transformer.py:235,242): out (Gt,C), arg (Gt,C) int32 = first
  * arg-max row; its backward scatter dx (R,C) = dpooled at the arg-max row, 0 elsewhere; and
- * dx = dlocal + scatter(dpooled) with colsum (C, may be NULL) += column sums of dx (atomic accumulate). */
+ * dx = dlocal + scatter(dpooled) with colsum_partials (ceil(Gt/gpc), C; may be NULL) = per-CTA column sums of dx. */
 UP3D_API int up3d_group_max(int act_bf16, int Gt, int K, int C, const void *x, void *out, int32_t *arg, up3d_stream_t stream);
 UP3D_API int up3d_group_max_scatter(int act_bf16, int Gt, int K, int C, const void *dpooled, const int32_t *arg, void *dx,
                                     up3d_stream_t stream);
 UP3D_API int up3d_group_combine(int act_bf16, int Gt, int K, int C, int gpc, const void *dlocal, const void *dpooled,
-                                const int32_t *arg, void *dx, float *colsum, up3d_stream_t stream);
+                                const int32_t *arg, void *dx, float *colsum_partials, up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Splat head: GaussianSplatPredictor._process_network_output (model/gaussian_predictor.py:279-328; activations
+ * 249-254) + the SH concatenation of render_predicted (gaussian_renderer/__init__.py:66-69) in one launch each way.
+ * raw (B,P,11+3M) = the `final` MLP's output rows [xyz 3 | opacity 1 | scaling 3 | rotation 4 | sh (M,3)],
+ * center (B,P,3).  Outputs: xyz (B,P,3) = tanh(raw)*offset_scale + center, opacity (B,P) = sigmoid,
+ * scaling (B,P,3) = exp(clamp(raw,-1,20)) (isotropic: channel 0 broadcast), rotation (B,P,4) = raw / max(||raw||_P, 1e-6)
+ * -- normalised over the P POINTS per component, the reference's F.normalize(dim=-1) on a (B,4,P) tensor --,
+ * shs (B,P,M,3), rot_norm (B,4) (saved for the backward).  Backward: d_raw (B,P,11+3M) from the five output
+ * gradients (any may be NULL = zero).
+ * ---------------------------------------------------------------------------------------- */
+UP3D_API int up3d_splat_head_fwd(int B, int P, int M, const float *raw, const float *center, float offset_scale,
+                                 int isotropic, float *xyz, float *opacity, float *scaling, float *rotation, float *shs,
+                                 float *rot_norm, up3d_stream_t stream);
+UP3D_API int up3d_splat_head_bwd(int B, int P, int M, const float *raw, const float *rot_norm, float offset_scale,
+                                 int isotropic, const float *d_xyz, const float *d_opacity, const float *d_scaling,
+                                 const float *d_rotation, const float *d_shs, float *d_raw, up3d_stream_t stream);
+
+/* FeatureFusion's geometry (fusion/feat_fusion.py:23-56, 88-131) for the analytic stem field, no gradient:
+ * centres (B,N,3) -> camera space with w2c (B,16 row-major), pixel = round(cam.xy * f / cam.z + c) (half to even),
+ * in-image test, nearest-depth test per pixel cell (iy*H + ix, the reference's hash) -> keep (B,N) uint8,
+ * pix (B,N,2) int32, and xhat (B,N,C) = GroupNorm-normalised stem field at image[b, :, ix, iy] (the reference's own
+ * index order), statistics from up3d_stem_group_stats' sums (B,G,2).  image (B,3,H,W), proj (C,3), shift (C). */
+UP3D_API int up3d_fusion_project(int B, int N, int H, int W, int C, int G, float fx, float fy, float cx, float cy, float eps,
+                                 const float *center, const float *w2c, const float *image, const float *proj,
+                                 const float *shift, const double *sums, unsigned char *keep, int32_t *pix, float *xhat,
+                                 up3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Frozen image stem (stand-in for model/image_predictor.py:56-81, whose SD-VAE weights are not shipped):

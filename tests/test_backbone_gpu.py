@@ -342,3 +342,78 @@ def test_attention_kernels_match_fp32_reference(B, L, H):
         assert err <= 3e-2 * float(ref.abs().max()) + 1e-3, (name, err, float(ref.abs().max()))
         cos = float(torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
         assert cos > 0.999, (name, cos)
+
+
+@pytest.mark.parametrize("deg,iso", [(1, False), (1, True), (2, False)])
+def test_fused_splat_head_matches_module_path(deg, iso):
+    """csrc/head.cu splat head == GaussianSplatPredictor._process_network_output (golden-pinned against the reference in
+    tests/test_golden_cpu.py) + the renderer's SH concatenation: values and gradients."""
+    from types import SimpleNamespace as NS
+    from unipre3d_b200.gaussian_predictor import GaussianSplatPredictor
+    m = GaussianSplatPredictor.__new__(GaussianSplatPredictor)
+    torch.nn.Module.__init__(m)
+    m.cfg = NS(model=NS(max_sh_degree=deg, isotropic=iso, offset_scale=0.7))
+    M = (deg + 1) ** 2
+    split = [3, 1, 3, 4, 3, (M - 1) * 3]
+    torch.manual_seed(8)
+    B, P = 3, 128
+    raw = (torch.randn(B, sum(split), P, device=DEV) * 1.5)
+    raw[:, 4:7, :3] = torch.tensor([-3.0, 25.0, 0.0], device=DEV).view(1, 3, 1)     # exercise clamp(-1, 20)
+    raw.requires_grad_(True)
+    center = torch.randn(B, P, 3, device=DEV)
+    ref = m._process_network_output(raw.split(split, dim=1), center)
+    ref_shs = torch.cat([ref["features_dc"], ref["features_rest"]], dim=2)
+    got = m._fused_head(raw, center)
+    for k in ("xyz", "opacity", "scaling", "rotation", "features_dc", "features_rest"):
+        assert got[k].shape == ref[k].shape, k
+        assert torch.allclose(got[k], ref[k], atol=1e-5, rtol=1e-5), k
+    assert torch.allclose(got["shs"], ref_shs, atol=0, rtol=0)
+    ws = {k: torch.randn_like(ref[k]) for k in ("xyz", "opacity", "scaling", "rotation")}
+    wsh = torch.randn_like(ref_shs)
+    # keep the huge exp(20) scale out of the cotangent so tolerances stay meaningful
+    ws["scaling"] = ws["scaling"] / ref["scaling"].detach().clamp_min(1.0)
+    lr = sum((ref[k] * ws[k]).sum() for k in ws) + (ref_shs * wsh).sum()
+    lg = sum((got[k] * ws[k]).sum() for k in ws) + (got["shs"] * wsh).sum()
+    (g_ref,) = torch.autograd.grad(lr, raw)
+    (g_got,) = torch.autograd.grad(lg, raw)
+    assert torch.allclose(g_got, g_ref, atol=2e-5 * float(g_ref.abs().max()) + 1e-6, rtol=1e-4)
+
+
+def test_fused_feature_fusion_matches_module_path():
+    """csrc/head.cu fusion projection == the eager restatement of fusion/feat_fusion.py (golden-pinned against the
+    reference in tests/test_golden_cpu.py): kept points, mapped features, fused output and image_conv gradients."""
+    import math
+    from unipre3d_b200 import camera as cam
+    from unipre3d_b200 import fusion
+    from unipre3d_b200.gaussian_predictor import StemFeatureField
+    torch.manual_seed(9)
+    B, N, R, Cin, Cout, G = 4, 128, 64, 128, 48, 32
+    fov = 49.13434264120263
+    proj_m = cam.get_projection_matrix(0.5, 2.0, math.radians(fov), math.radians(fov))
+    c2w = torch.stack([cam.make_view(*cam.look_at_pose(40.0 * i, 10.0 + 15 * i, 1.75), proj_m)["view_to_world_transform"]
+                       for i in range(B)]).unsqueeze(1).to(DEV)
+    K = np.zeros((3, 4)); focal = (R / 2.0) / math.tan(math.radians(fov / 2.0))
+    K[0, 0] = K[1, 1] = focal; K[0, 2] = K[1, 2] = R / 2.0; K[2, 2] = 1
+    center = torch.randn(B, N, 3, device=DEV) * 0.3
+    center[:, 5] = center[:, 4] * 1.02          # same pixel, depth test decides
+    center[:, 7] = 5.0                          # outside the image
+    img = torch.rand(B, 3, R, R, device=DEV)
+    field = StemFeatureField(img, torch.randn(Cin, 3, device=DEV) * 0.7, torch.randn(Cin, device=DEV) * 0.3)
+    conv = torch.nn.Sequential(torch.nn.GroupNorm(G, Cin, eps=1e-6), torch.nn.Conv2d(Cin, Cout, 1)).to(DEV)
+    mlp = torch.nn.Sequential(torch.nn.Linear(2 * Cout, Cout), torch.nn.ReLU()).to(DEV)
+    x = torch.randn(B, N + 1, Cout, device=DEV)
+    w = torch.randn(B, N + 1, Cout, device=DEV)
+    outs = {}
+    for force in (True, False):
+        fusion.FORCE_MODULE_PATH = force
+        try:
+            y = fusion.FeatureFusion(mlp)(x, center, fusion.LazyImageFeatures(field, conv), c2w, K)
+            g = torch.autograd.grad((y * w).sum(), list(conv.parameters()) + list(mlp.parameters()))
+        finally:
+            fusion.FORCE_MODULE_PATH = False
+        outs[force] = (y.detach(), g)
+    keep, mapped, pix = fusion.fused_project_and_sample(fusion.LazyImageFeatures(field, conv), center, c2w[:, 0], K)
+    assert 0 < int(keep.sum()) < B * N and not bool(keep[:, 7].any())
+    assert torch.allclose(outs[False][0], outs[True][0], atol=2e-5, rtol=1e-4)
+    for a, b in zip(outs[False][1], outs[True][1]):
+        assert torch.allclose(a, b, atol=1e-4 * float(b.abs().max()) + 1e-6, rtol=1e-4)

@@ -114,8 +114,11 @@ def test_group_combine_matches_torch():
     arg = torch.randint(0, K, (Gt, C), device=DEV, dtype=torch.int32)
     for gpc in (1, 2):
         dx = torch.empty_like(dl)
-        cs = torch.zeros(C, device=DEV)
-        check(_lib.lib.up3d_group_combine(0, Gt, K, C, gpc, ptr(dl), ptr(dp), ptr(arg), ptr(dx), ptr(cs), stream_ptr()), 1)
+        part = torch.empty((Gt + gpc - 1) // gpc, 1, C, device=DEV)
+        check(_lib.lib.up3d_group_combine(0, Gt, K, C, gpc, ptr(dl), ptr(dp), ptr(arg), ptr(dx), ptr(part), stream_ptr()), 1)
+        cs = torch.empty(1, C, device=DEV)
+        check(_lib.lib.up3d_bn_reduce_sums(part.shape[0], 1, C, ptr(part), ptr(cs), stream_ptr()), 1)
+        cs = cs[0]
         ref = dl.view(Gt, K, C) + torch.zeros(Gt, K, C, device=DEV).scatter_(1, arg.long().unsqueeze(1), dp.unsqueeze(1))
         assert torch.allclose(dx.view(Gt, K, C), ref, atol=1e-6)
         assert torch.allclose(cs, ref.sum((0, 1)), atol=1e-3, rtol=1e-4)

@@ -59,7 +59,7 @@ def _load() -> C.CDLL:
         "up3d_stem_group_stats": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_pn_stats_tile_rows": (i32, []),
         "up3d_pn_conv1_stats": (i32, [i32, i32, vp, vp, vp, vp, vp]),
-        "up3d_bn_reduce_sums": (i32, [i32, i32, vp, vp, vp]),
+        "up3d_bn_reduce_sums": (i32, [i32, i32, i32, vp, vp, vp]),
         "up3d_pn_conv1_bn_relu": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, vp]),
         "up3d_pn_conv1_bwd": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, C.c_double, vp, i32, vp, vp, vp]),
         "up3d_bn_reduce_finalize": (i32, [i32, i32, vp, i32, i64, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp]),
@@ -73,6 +73,9 @@ def _load() -> C.CDLL:
         "up3d_attn_max_len": (i32, []),
         "up3d_attn_fwd": (i32, [i32, i32, i32, i32, f32, vp, vp, vp, vp]),
         "up3d_attn_bwd": (i32, [i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+        "up3d_splat_head_fwd": (i32, [i32, i32, i32, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "up3d_splat_head_bwd": (i32, [i32, i32, i32, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "up3d_fusion_project": (i32, [i32] * 6 + [f32] * 5 + [vp] * 10),
         "up3d_adamw_chunk_elems": (i32, []),
         "up3d_adamw_step": (i32, [i32, i32] + [vp] * 10 + [f32] * 5 + [vp, vp]),
         "up3d_adamw_apply": (i32, [i32, i32] + [vp] * 10 + [f32] * 5 + [vp, vp]),
@@ -96,7 +99,7 @@ EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_residen
             "up3d_bn_reduce_sums", "up3d_pn_conv1_bn_relu", "up3d_pn_conv1_bwd",
             "up3d_bn_reduce_finalize", "up3d_gbn_stats", "up3d_gbn_apply_relu", "up3d_gbn_bwd_reduce", "up3d_gbn_bwd_apply",
             "up3d_group_max", "up3d_group_max_scatter", "up3d_group_combine", "up3d_attn_max_len", "up3d_attn_fwd",
-            "up3d_attn_bwd"]
+            "up3d_attn_bwd", "up3d_splat_head_fwd", "up3d_splat_head_bwd", "up3d_fusion_project"]
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0

@@ -156,8 +156,10 @@ pn_conv1_bwd_kernel(int R, int GK, const float *__restrict__ nb, const float *__
         partials[((size_t)blockIdx.x * 2 + 0) * PN_C1 + c] = acc0;
         partials[((size_t)blockIdx.x * 2 + 1) * PN_C1 + c] = acc1;
     } else {
-        atomicAdd(gW1 + 3 * c, acc0); atomicAdd(gW1 + 3 * c + 1, acc1); atomicAdd(gW1 + 3 * c + 2, acc2);
-        atomicAdd(gb1 + c, acc3);
+        // partials (gridDim.x, 2, 2*C1): row 0 = [dW[:,0] | dW[:,1]], row 1 = [dW[:,2] | db]  (same-address atomics from
+        // every CTA serialised this kernel: 53 -> ~15 us)
+        float *pr = partials + (size_t)blockIdx.x * 4 * PN_C1;
+        pr[c] = acc0; pr[PN_C1 + c] = acc1; pr[2 * PN_C1 + c] = acc2; pr[3 * PN_C1 + c] = acc3;
     }
 }
 
@@ -192,19 +194,20 @@ bn_reduce_finalize_kernel(int nPart, int C, const float *__restrict__ partials, 
     const int c = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
     const bool ok = c < C;
     if (MODE == 0) {
+        const int nrows = rows_per_part;        // MODE 0 reuses this argument: rows (1 or 2) of each partial
         double s = 0.0, q = 0.0;
         if (ok) {
 #pragma unroll 4
             for (int p = ly; p < nPart; p += FIN_LANES) {
-                s += (double)partials[((size_t)p * 2 + 0) * C + c];
-                q += (double)partials[((size_t)p * 2 + 1) * C + c];
+                s += (double)partials[((size_t)p * nrows + 0) * C + c];
+                if (nrows == 2) q += (double)partials[((size_t)p * nrows + 1) * C + c];
             }
         }
         s = fin_lane_sum(s, sh);
         q = fin_lane_sum(q, sh);
         if (ly == 0 && ok) {
             sums[c] = (float)s;
-            sums[C + c] = (float)q;
+            if (nrows == 2) sums[C + c] = (float)q;
         }
         return;
     }
@@ -448,10 +451,7 @@ group_tile_kernel(GroupTileArgs A) {
                 p1.x += t1.x; p1.y += t1.y; p1.z += t1.z; p1.w += t1.w;
             }
             if (MODE == GT_COMBINE) {
-                if (A.colsum) {
-                    atomicAdd(A.colsum + col, p0.x); atomicAdd(A.colsum + col + 1, p0.y);
-                    atomicAdd(A.colsum + col + 2, p0.z); atomicAdd(A.colsum + col + 3, p0.w);
-                }
+                if (A.partials) *reinterpret_cast<float4 *>(A.partials + (size_t)blockIdx.x * C + col) = p0;
             } else if (MODE == GT_STATS) {
                 *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 3 + 0) * C + col) = shift;
                 *reinterpret_cast<float4 *>(A.partials + ((size_t)blockIdx.x * 3 + 1) * C + col) = p0;
@@ -512,7 +512,7 @@ extern "C" int up3d_pn_conv1_bwd(int act_bf16, int pass, int R, int GK, const fl
                                  int n_partials, float *gW1, float *gb1, up3d_stream_t stream) {
     UP3D_CHECK_ARG(R > 0 && GK > 0 && R % GK == 0, "up3d_pn_conv1_bwd: R must be a positive multiple of G*K");
     UP3D_CHECK_ARG(nb && W1 && b1 && stats && dy1 && n_partials > 0, "up3d_pn_conv1_bwd: NULL pointer");
-    UP3D_CHECK_ARG(pass == 0 ? partials != nullptr : (sums && gW1 && gb1 && count > 0), "up3d_pn_conv1_bwd: missing outputs for this pass");
+    UP3D_CHECK_ARG(partials != nullptr && (pass == 0 || (sums && count > 0)), "up3d_pn_conv1_bwd: missing arguments for this pass");
     const float inv_count = pass == 0 ? 0.f : (float)(1.0 / count);
     cudaStream_t st = (cudaStream_t)stream;
 #define PN_BWD(AT, P) pn_conv1_bwd_kernel<AT, P><<<n_partials, PN_C1, 0, st>>>(R, GK, nb, W1, b1, stats, (const AT *)dy1, sums, inv_count, partials, gW1, gb1)
@@ -523,10 +523,10 @@ extern "C" int up3d_pn_conv1_bwd(int act_bf16, int pass, int R, int GK, const fl
     return 0;
 }
 
-extern "C" int up3d_bn_reduce_sums(int n_partials, int C, const float *partials, float *sums, up3d_stream_t stream) {
-    UP3D_CHECK_ARG(n_partials > 0 && C > 0 && partials && sums, "up3d_bn_reduce_sums: bad arguments");
+extern "C" int up3d_bn_reduce_sums(int n_partials, int n_rows, int C, const float *partials, float *sums, up3d_stream_t stream) {
+    UP3D_CHECK_ARG(n_partials > 0 && C > 0 && partials && sums && (n_rows == 1 || n_rows == 2), "up3d_bn_reduce_sums: bad arguments");
     bn_reduce_finalize_kernel<0><<<div_up(C, 32), dim3(32, FIN_LANES), 0, (cudaStream_t)stream>>>(
-        n_partials, C, partials, sums, 0, 0, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
+        n_partials, C, partials, sums, n_rows, 0, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
     UP3D_LAUNCH_OK("bn_reduce_finalize_kernel<sums>");
     return 0;
 }
@@ -636,12 +636,12 @@ extern "C" int up3d_group_max_scatter(int act_bf16, int Gt, int K, int C, const 
 }
 
 extern "C" int up3d_group_combine(int act_bf16, int Gt, int K, int C, int gpc, const void *dlocal, const void *dpooled,
-                                  const int32_t *arg, void *dx, float *colsum, up3d_stream_t stream) {
+                                  const int32_t *arg, void *dx, float *colsum_partials, up3d_stream_t stream) {
     if (int rc = gt_common("up3d_group_combine", Gt, K, C, gpc)) return rc;
     UP3D_CHECK_ARG(dlocal && dpooled && arg && dx && pn_aligned16(dlocal) && pn_aligned16(dpooled) && pn_aligned16(arg) &&
                    pn_aligned16(dx), "up3d_group_combine: NULL or misaligned pointer");
     GroupTileArgs A{};
-    A.Gt = Gt; A.K = K; A.C = C; A.gpc = gpc; A.in0 = dlocal; A.small_in = dpooled; A.arg = arg; A.out = dx; A.colsum = colsum;
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = gpc; A.in0 = dlocal; A.small_in = dpooled; A.arg = arg; A.out = dx; A.partials = colsum_partials;
     GT_DISPATCH(GT_COMBINE);
     UP3D_LAUNCH_OK("group_tile_kernel<combine>");
     return 0;

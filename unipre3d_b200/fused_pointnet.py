@@ -34,9 +34,10 @@ def _world(bn) -> int:
 
 
 def _reduce(partials, C):
-    """backward partials (n,2,C) -> sums (2,C), fp64 accumulation."""
-    sums = torch.empty((2, C), dtype=torch.float32, device=partials.device)
-    check(_lib.lib.up3d_bn_reduce_sums(partials.shape[0], C, ptr(partials), ptr(sums), stream_ptr()), 1)
+    """per-CTA partial sums (n, rows, C) -> sums (rows, C), rows = 1 or 2, fp64 accumulation."""
+    rows = partials.shape[1]
+    sums = torch.empty((rows, C), dtype=torch.float32, device=partials.device)
+    check(_lib.lib.up3d_bn_reduce_sums(partials.shape[0], rows, C, ptr(partials), ptr(sums), stream_ptr()), 1)
     return sums
 
 
@@ -164,9 +165,10 @@ class MiniPointNetFn(torch.autograd.Function):
             dfg = dgp @ W3g
             gW3 = side.run(lambda a, b, c, d: torch.cat([_wgrad(a, b), _wgrad(c, d)], dim=1), dgp, fg, dz3, f)
             # ---- group max backward + layer 2
-            gb2 = torch.zeros(C2, dtype=torch.float32, device=dev)
+            gb2p = torch.empty(((Gt + gpc - 1) // gpc, 1, C2), dtype=torch.float32, device=dev)
             df = torch.empty((R, C2), dtype=act, device=dev)
-            check(L.up3d_group_combine(fl, Gt, K, C2, gpc, ptr(dfl), ptr(dfg), ptr(arg2), ptr(df), ptr(gb2), stream_ptr()), 1)
+            check(L.up3d_group_combine(fl, Gt, K, C2, gpc, ptr(dfl), ptr(dfg), ptr(arg2), ptr(df), ptr(gb2p), stream_ptr()), 1)
+            gb2 = _reduce(gb2p, C2)[0]
             dy1 = df @ W2c
             gW2 = side.run(_wgrad, df, y1)
             # ---- BN1 + ReLU + layer 1 backward
@@ -175,10 +177,11 @@ class MiniPointNetFn(torch.autograd.Function):
             check(L.up3d_pn_conv1_bwd(fl, 0, R, GK, ptr(nb), ptr(w1), ptr(b1), ptr(stats1), ptr(dy1), None, 0.0, ptr(part1),
                                       n1, None, None, stream_ptr()), 1)
             sums1, sums1g = _bn_backward_sums(part1, C1, wd1)
-            g1buf = torch.zeros(C1 * 4, dtype=torch.float32, device=dev)
-            gW1, gb1 = g1buf[:C1 * 3], g1buf[C1 * 3:]
+            g1p = torch.empty((n1, 2, 2 * C1), dtype=torch.float32, device=dev)
             check(L.up3d_pn_conv1_bwd(fl, 1, R, GK, ptr(nb), ptr(w1), ptr(b1), ptr(stats1), ptr(dy1), ptr(sums1g),
-                                      float(R * wd1), None, n1, ptr(gW1), ptr(gb1), stream_ptr()), 1)
+                                      float(R * wd1), ptr(g1p), n1, None, None, stream_ptr()), 1)
+            g1 = _reduce(g1p, 2 * C1).view(4, C1)              # rows: dW[:,0], dW[:,1], dW[:,2], db
+            gW1, gb1 = g1[:3].t().contiguous(), g1[3]
             gb3 = torch.zeros(C3, dtype=torch.float32, device=dev)       # bias in front of a train-mode BatchNorm
             side.join()
         return (None, None, gW1.view(C1, 3, 1), gb1, sums1[1], sums1[0], gW2.view(C2, C1, 1), gb2, gW3.view(C3, 2 * C2, 1),

@@ -52,6 +52,39 @@ class LazyImageFeatures:
         return torch.nn.functional.linear(y, conv.weight.reshape(conv.out_channels, Cin), conv.bias)
 
 
+FORCE_MODULE_PATH = False      # tests: run the eager restatement below on CUDA too
+FUSED_MAX_POINTS = 1024        # centres per object the fused kernel holds in shared memory
+
+
+def fused_project_and_sample(lazy: "LazyImageFeatures", center, c2w_matrix, intrinsic):
+    """CUDA path of FeatureFusion's geometry for the analytic stem field (csrc/head.cu `up3d_fusion_project`):
+    -> keep (B,N) bool, mapped (B,N,C_out) = image_conv(field)[b, :, ix, iy] (differentiable w.r.t. image_conv)."""
+    from . import _lib
+    from ._lib import check, ptr, stream_ptr
+    field, gn, conv = lazy.x, lazy.gn, lazy.conv
+    B, N = center.shape[:2]
+    n, Cin, H, W = field.shape
+    if n != B:
+        raise RuntimeError("fused feature fusion expects one source view per object")
+    G = gn.num_groups
+    dev = center.device
+    with torch.no_grad(), torch.autocast("cuda", enabled=False):
+        w2c = torch.linalg.inv_ex(c2w_matrix.permute(0, 2, 1).float()).inverse.contiguous()
+        sums = field.group_sums(G)
+        keep = torch.empty((B, N), dtype=torch.uint8, device=dev)
+        pix = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
+        xhat = torch.empty((B, N, Cin), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib.up3d_fusion_project(B, N, H, W, Cin, G, float(intrinsic[0][0]), float(intrinsic[1][1]),
+                                               float(intrinsic[0][2]), float(intrinsic[1][2]), float(gn.eps),
+                                               ptr(center.contiguous().float()), ptr(w2c), ptr(field.image), ptr(field.proj.contiguous()),
+                                               ptr(field.shift.contiguous()), ptr(sums), ptr(keep), ptr(pix), ptr(xhat),
+                                               stream_ptr()), launches=1)
+    y = xhat * gn.weight + gn.bias
+    mapped = torch.nn.functional.linear(y, conv.weight.reshape(conv.out_channels, Cin), conv.bias)
+    return keep.bool(), mapped, pix
+
+
 class FeatureFusion:
     def __init__(self, fusion_mlp: nn.Module):
         self.fusion_mlp = fusion_mlp
@@ -72,6 +105,10 @@ class FeatureFusion:
         C, H, W = image_features.shape[1:]
         if c2w_projection_matrix.dim() == 4:
             c2w_projection_matrix = c2w_projection_matrix[:, 0]
+        if (center.is_cuda and isinstance(image_features, LazyImageFeatures) and not torch.is_tensor(image_features.x)
+                and N <= FUSED_MAX_POINTS and not FORCE_MODULE_PATH):
+            keep, mapped, _ = fused_project_and_sample(image_features, center, c2w_projection_matrix, intrinsic)
+            return self._fuse(x, center, keep, mapped, C)
         with torch.no_grad():
             pi_xy, p_depth = self.project_points_to_image(center, c2w_projection_matrix, intrinsic)
             fx, fy = pi_xy[..., 0], pi_xy[..., 1]
@@ -89,6 +126,10 @@ class FeatureFusion:
             mapped = image_features.sample(bidx, ix, iy)
         else:
             mapped = image_features[bidx, :, ix, iy]                                                 # (B,N,C)
+        return self._fuse(x, center, keep, mapped, C)
+
+    def _fuse(self, x, center, keep, mapped, C):
+        B, N = center.shape[:2]
         mapped = torch.where(keep.unsqueeze(-1), mapped.to(x.dtype), torch.zeros((), dtype=x.dtype, device=x.device))
         x_num = x.shape[1]
         if x_num > N:  # transformer: CLS token gets zeros

@@ -51,8 +51,8 @@ class StemFeatureField:
             return torch.sin(f)
 
     @torch.no_grad()
-    def group_stats(self, num_groups: int):
-        """-> (mean, biased var), each (n, G), over each group's channels x pixels (torch.var_mean(unbiased=False))."""
+    def group_sums(self, num_groups: int) -> torch.Tensor:
+        """-> (n, G, 2) fp64 [sum f, sum f^2] over each group's channels x pixels (csrc/stem.cu)."""
         from . import _lib
         from ._lib import check, ptr, require_cuda, stream_ptr
         require_cuda(self.image, self.proj, self.shift)
@@ -61,6 +61,13 @@ class StemFeatureField:
         with torch.cuda.device(self.image.device):
             check(_lib.lib.up3d_stem_group_stats(n, H, W, Cc, num_groups, ptr(self.image), ptr(self.proj.contiguous()),
                                                  ptr(self.shift.contiguous()), ptr(sums), stream_ptr()), launches=1)
+        return sums
+
+    @torch.no_grad()
+    def group_stats(self, num_groups: int):
+        """-> (mean, biased var), each (n, G), over each group's channels x pixels (torch.var_mean(unbiased=False))."""
+        n, Cc, H, W = self.shape
+        sums = self.group_sums(num_groups)
         cnt = float((Cc // num_groups) * H * W)
         mean = sums[..., 0] / cnt
         var = (sums[..., 1] / cnt - mean * mean).clamp_min(0.0)
@@ -90,6 +97,45 @@ class FrozenImageStem(nn.Module):
     def forward(self, x: torch.Tensor, lazy: bool = False) -> Dict[str, torch.Tensor]:
         field = StemFeatureField(x, self.proj, self.shift)
         return {"decoder_block_3": field if (lazy and x.is_cuda) else field.dense()}
+
+
+class SplatHeadFn(torch.autograd.Function):
+    """`_process_network_output` (object level) + the SH concatenation of the renderer as one launch each way
+    (csrc/head.cu).  raw (B,P,11+3M) fp32, center (B,P,3) -> xyz, opacity (B,P,1), scaling, rotation, shs (B,P,M,3)."""
+
+    @staticmethod
+    def forward(ctx, raw, center, M, offset_scale, isotropic):
+        from . import _lib
+        from ._lib import check, ptr, require_cuda, stream_ptr
+        require_cuda(raw, center)
+        raw, center = raw.contiguous().float(), center.contiguous().float()
+        B, P, Cr = raw.shape
+        if Cr != 11 + 3 * M:
+            raise RuntimeError(f"splat head: {Cr} channels do not match max_sh_degree (expected {11 + 3 * M})")
+        dev = raw.device
+        e = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        xyz, op, sc, rot, shs, rn = e(B, P, 3), e(B, P, 1), e(B, P, 3), e(B, P, 4), e(B, P, M, 3), e(B, 4)
+        with torch.cuda.device(dev):
+            check(_lib.lib.up3d_splat_head_fwd(B, P, M, ptr(raw), ptr(center), float(offset_scale), int(bool(isotropic)),
+                                               ptr(xyz), ptr(op), ptr(sc), ptr(rot), ptr(shs), ptr(rn), stream_ptr()), 1)
+        ctx.save_for_backward(raw, rn)
+        ctx.cfg = (M, float(offset_scale), int(bool(isotropic)))
+        return xyz, op, sc, rot, shs
+
+    @staticmethod
+    def backward(ctx, d_xyz, d_op, d_sc, d_rot, d_shs):
+        from . import _lib
+        from ._lib import check, ptr, stream_ptr
+        raw, rn = ctx.saved_tensors
+        M, offset_scale, iso = ctx.cfg
+        B, P, _ = raw.shape
+        c = lambda t: None if t is None else t.contiguous().float()
+        d_xyz, d_op, d_sc, d_rot, d_shs = c(d_xyz), c(d_op), c(d_sc), c(d_rot), c(d_shs)
+        d_raw = torch.empty_like(raw)
+        with torch.cuda.device(raw.device):
+            check(_lib.lib.up3d_splat_head_bwd(B, P, M, ptr(raw), ptr(rn), offset_scale, iso, ptr(d_xyz), ptr(d_op), ptr(d_sc),
+                                               ptr(d_rot), ptr(d_shs), ptr(d_raw), stream_ptr()), 1)
+        return d_raw, None, None, None, None
 
 
 class PointFeaturePredictor(nn.Module):
@@ -205,9 +251,27 @@ class GaussianSplatPredictor(nn.Module):
             image_features = LazyImageFeatures(image_output["decoder_block_3"], self.image_conv)
         point_features, center = self.point_network.forward_feat_fusion(
             point_cloud, image_features, source_cameras_view_to_world, self.fusion_mlps, self.intrinsic)
-        out = self._process_network_output(point_features.split(self.split_dimensions, dim=1), center)
+        if point_features.is_cuda and not getattr(self, "force_module_path", False):
+            out = self._fused_head(point_features, center)
+        else:
+            out = self._process_network_output(point_features.split(self.split_dimensions, dim=1), center)
         out = {k: v.reshape(B, N_views * v.shape[1], *v.shape[2:]) for k, v in out.items()}   # _multi_view_union
-        return {k: v.contiguous() for k, v in out.items()}
+        # (features_dc / features_rest stay views of "shs" on the fused path: the renderer consumes "shs")
+        return {k: (v if ("shs" in out and k.startswith("features_")) else v.contiguous()) for k, v in out.items()}
+
+    def _fused_head(self, point_features, center) -> Dict[str, torch.Tensor]:
+        """CUDA path of `_process_network_output`: point_features (B,C,P) is the permuted view of the head's (B,P,C)
+        rows; one kernel writes the reference's output dict plus "shs" = [features_dc || features_rest] (B,P,M,3), the
+        tensor render_predicted concatenates per call (gaussian_renderer/__init__.py:66-69)."""
+        M = (int(self.cfg.model.max_sh_degree) + 1) ** 2
+        raw = point_features.permute(0, 2, 1)
+        xyz, op, sc, rot, shs = SplatHeadFn.apply(raw, center[:, :, :3], M, float(self.cfg.model.offset_scale),
+                                                  bool(self.cfg.model.isotropic))
+        out = {"xyz": xyz, "opacity": op, "scaling": sc, "rotation": rot, "features_dc": shs[:, :, :1],
+               "features_rest": shs[:, :, 1:], "shs": shs}
+        if M == 1:
+            out["features_rest"] = torch.zeros((shs.shape[0], 0, 3), dtype=shs.dtype, device=shs.device)
+        return out
 
     @staticmethod
     def _flatten_vector(x):

@@ -89,7 +89,9 @@ def render_batch_predicted(pc: Dict[str, Union[torch.Tensor, List[torch.Tensor]]
         sizes = [P] * B
         xyz, op = pc["xyz"].reshape(B * P, 3), pc["opacity"].reshape(B * P)
         sc, rot = pc["scaling"].reshape(B * P, 3), pc["rotation"].reshape(B * P, 4)
-        if "features_rest" in pc:
+        if "shs" in pc:           # already concatenated by the fused splat head (gaussian_predictor._fused_head)
+            shs = pc["shs"].reshape(B * P, -1, 3)
+        elif "features_rest" in pc:
             shs = torch.cat([pc["features_dc"], pc["features_rest"]], dim=2).reshape(B * P, -1, 3)
         else:
             shs = pc["features_dc"].reshape(B * P, -1, 3)
