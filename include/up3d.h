@@ -244,22 +244,25 @@ UP3D_API int up3d_attn_bwd(int B, int L, int H, int D, float scale, const void *
  *          fp64 sum-of-squares accumulator | float step | float total_norm | float clip_coef | float found_inf |
  *          uint32 ticket | pad.
  * A non-finite total norm leaves parameters, moments and the step counter untouched.
+ * grad_scale (> 0) multiplies every gradient on the fly (1/world when the gradient buffers hold the SUM over the
+ * data-parallel ranks; 1 otherwise): the norm, the clipping and the update all see grad_scale * g.
  * up3d_adamw_step = up3d_grad_sumsq (1 launch) + up3d_adamw_apply (1 launch; its last CTA advances the step
  * counter and clears the accumulator), exported separately so each pass can be timed on its own.
  * ---------------------------------------------------------------------------------------- */
 UP3D_API int up3d_adamw_chunk_elems(void);
 UP3D_API int up3d_grad_sumsq(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
-                             const int64_t *numel, const float *const *grads, void *state, up3d_stream_t stream);
+                             const int64_t *numel, const float *const *grads, float grad_scale, void *state,
+                             up3d_stream_t stream);
 UP3D_API int up3d_adamw_apply(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
                               const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
                               float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
-                              float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
-                              up3d_stream_t stream);
+                              float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                              void *state, up3d_stream_t stream);
 UP3D_API int up3d_adamw_step(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
                              const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
                              float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
-                             float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
-                             up3d_stream_t stream);
+                             float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                             void *state, up3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Mini-PointNet of the tokenizer (openpoints/models/backbone/transformer.py:210-243 `Encoder`): the memory-bound

@@ -77,9 +77,9 @@ def _load() -> C.CDLL:
         "up3d_splat_head_bwd": (i32, [i32, i32, i32, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp, vp]),
         "up3d_fusion_project": (i32, [i32] * 6 + [f32] * 5 + [vp] * 10),
         "up3d_adamw_chunk_elems": (i32, []),
-        "up3d_adamw_step": (i32, [i32, i32] + [vp] * 10 + [f32] * 5 + [vp, vp]),
-        "up3d_adamw_apply": (i32, [i32, i32] + [vp] * 10 + [f32] * 5 + [vp, vp]),
-        "up3d_grad_sumsq": (i32, [i32, i32] + [vp] * 6),
+        "up3d_adamw_step": (i32, [i32, i32] + [vp] * 10 + [f32] * 6 + [vp, vp]),
+        "up3d_adamw_apply": (i32, [i32, i32] + [vp] * 10 + [f32] * 6 + [vp, vp]),
+        "up3d_grad_sumsq": (i32, [i32, i32] + [vp] * 4 + [f32, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

@@ -280,7 +280,8 @@ constexpr int ADAM_CHUNK = 4096;     // elements per chunk (16 KB fp32): 256 thr
 
 __global__ void __launch_bounds__(256)
 grad_sumsq_kernel(int n_chunks, const int *__restrict__ chunk_tensor, const int *__restrict__ chunk_start,
-                  const long long *__restrict__ numel, const float *const *__restrict__ grads, double *__restrict__ acc) {
+                  const long long *__restrict__ numel, const float *const *__restrict__ grads, float grad_scale,
+                  double *__restrict__ acc) {
     __shared__ float s_part[8];
     float local = 0.f;
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
@@ -309,12 +310,12 @@ grad_sumsq_kernel(int n_chunks, const int *__restrict__ chunk_tensor, const int 
         v += __shfl_xor_sync(0xffu, v, 4);
         v += __shfl_xor_sync(0xffu, v, 2);
         v += __shfl_xor_sync(0xffu, v, 1);
-        if (threadIdx.x == 0) atomicAdd(acc, (double)v);
+        if (threadIdx.x == 0) atomicAdd(acc, (double)v * (double)grad_scale * (double)grad_scale);
     }
 }
 
 // state (device, 32 bytes):  fp64 sum-of-squares accumulator | float step, total_norm, clip_coef, found_inf | u32 ticket | pad
-struct AdamHyper { float beta1, beta2, eps, weight_decay, max_norm; };
+struct AdamHyper { float beta1, beta2, eps, weight_decay, max_norm, grad_scale; };
 
 __device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g, float lr, float wd, float b1, float b2,
                                           float eps, float step_size, float inv_bc2_sqrt) {
@@ -337,7 +338,7 @@ adamw_kernel(int n_chunks, const int *__restrict__ chunk_tensor, const int *__re
     const float total = (float)sqrt(acc[0]);
     const bool bad = !isfinite(total);
     float coef = h.max_norm > 0.f ? h.max_norm / (total + 1e-6f) : 1.f;   // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
-    coef = fminf(coef, 1.f);
+    coef = fminf(coef, 1.f) * h.grad_scale;            // gradients enter as grad_scale * g (1/world under data parallelism)
     const float t = state[0] + 1.f;
     const float bc1 = 1.f - powf(h.beta1, t), bc2 = 1.f - powf(h.beta2, t);
     const float inv_bc2_sqrt = rsqrtf(bc2);
@@ -391,7 +392,7 @@ adamw_kernel(int n_chunks, const int *__restrict__ chunk_tensor, const int *__re
         unsigned *ticket = reinterpret_cast<unsigned *>(state + 4);
         if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
             state[1] = total;
-            state[2] = bad ? 0.f : coef;
+            state[2] = bad ? 0.f : coef / h.grad_scale;
             state[3] = bad ? 1.f : 0.f;
             if (!bad) state[0] = t;            // the step counter only advances on applied steps
             acc[0] = 0.0;                      // ready for the next step's sum of squares
@@ -540,14 +541,15 @@ static int adamw_check(int n_tensors, int n_chunks, const void *a, const void *b
 }
 
 extern "C" int up3d_grad_sumsq(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
-                               const int64_t *numel, const float *const *grads, void *state, up3d_stream_t stream) {
+                               const int64_t *numel, const float *const *grads, float grad_scale, void *state,
+                               up3d_stream_t stream) {
     if (int rc = adamw_check(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, state)) return rc;
     if (n_tensors == 0 || n_chunks == 0) return 0;
     UP3D_CHECK_ARG(grads != nullptr, "up3d_grad_sumsq: NULL pointer");
     static_assert(sizeof(long long) == sizeof(int64_t), "int64");
     const int grid = min(n_chunks, UP3D_NUM_SMS * 8);
     grad_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_chunks, chunk_tensor, chunk_start, (const long long *)numel,
-                                                             grads, (double *)state);
+                                                             grads, grad_scale, (double *)state);
     UP3D_LAUNCH_OK("grad_sumsq_kernel");
     return 0;
 }
@@ -555,13 +557,14 @@ extern "C" int up3d_grad_sumsq(int n_tensors, int n_chunks, const int32_t *chunk
 extern "C" int up3d_adamw_apply(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
                                 const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
                                 float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
-                                float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
-                                up3d_stream_t stream) {
+                                float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                                void *state, up3d_stream_t stream) {
     if (int rc = adamw_check(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, state)) return rc;
     if (n_tensors == 0 || n_chunks == 0) return 0;
     UP3D_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && group && lrs, "up3d_adamw_apply: NULL pointer");
+    UP3D_CHECK_ARG(grad_scale > 0.f, "up3d_adamw_apply: grad_scale must be positive");
     const int grid = min(n_chunks, UP3D_NUM_SMS * 8);
-    AdamHyper h{beta1, beta2, eps, weight_decay, max_norm};
+    AdamHyper h{beta1, beta2, eps, weight_decay, max_norm, grad_scale};
     adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_chunks, chunk_tensor, chunk_start, (const long long *)numel, params,
                                                         grads, exp_avg, exp_avg_sq, (__nv_bfloat16 *const *)bf16_shadows,
                                                         group, lrs, (double *)state, (float *)state + 2, h);
@@ -572,9 +575,9 @@ extern "C" int up3d_adamw_apply(int n_tensors, int n_chunks, const int32_t *chun
 extern "C" int up3d_adamw_step(int n_tensors, int n_chunks, const int32_t *chunk_tensor, const int32_t *chunk_start,
                                const int64_t *numel, float *const *params, const float *const *grads, float *const *exp_avg,
                                float *const *exp_avg_sq, void *const *bf16_shadows, const int32_t *group, const float *lrs,
-                               float beta1, float beta2, float eps, float weight_decay, float max_norm, void *state,
-                               up3d_stream_t stream) {
-    if (int rc = up3d_grad_sumsq(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, grads, state, stream)) return rc;
+                               float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                               void *state, up3d_stream_t stream) {
+    if (int rc = up3d_grad_sumsq(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, grads, grad_scale, state, stream)) return rc;
     return up3d_adamw_apply(n_tensors, n_chunks, chunk_tensor, chunk_start, numel, params, grads, exp_avg, exp_avg_sq,
-                            bf16_shadows, group, lrs, beta1, beta2, eps, weight_decay, max_norm, state, stream);
+                            bf16_shadows, group, lrs, beta1, beta2, eps, weight_decay, max_norm, grad_scale, state, stream);
 }

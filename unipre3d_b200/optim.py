@@ -25,6 +25,7 @@ class FusedClipAdamW(torch.optim.AdamW):
                  shadows: Optional[Dict[int, torch.Tensor]] = None):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.max_norm = float(max_norm)
+        self.grad_scale = 1.0          # gradients are read as grad_scale * p.grad (1/world when p.grad holds the rank SUM)
         self._shadows = shadows or {}
         self._built = False
         self._ring, self._ring_ev, self._ring_i, self._frozen = [], [], 0, []
@@ -158,7 +159,8 @@ class FusedClipAdamW(torch.optim.AdamW):
                                            ptr(self._numel), ptr(self._p_ptrs), ptr(self._g_ptrs), ptr(self._m_ptrs),
                                            ptr(self._v_ptrs), ptr(self._s_ptrs), ptr(self._group), ptr(self._lrs),
                                            float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"]),
-                                           float(g0["weight_decay"]), self.max_norm, ptr(self._state), stream_ptr()),
+                                           float(g0["weight_decay"]), self.max_norm, float(self.grad_scale),
+                                           ptr(self._state), stream_ptr()),
                   launches=2)
         return None
 
@@ -176,12 +178,13 @@ class FusedClipAdamW(torch.optim.AdamW):
         with torch.cuda.device(self._dev):
             for _ in range(reps):
                 ev[0].record()
-                check(L.up3d_grad_sumsq(*head, ptr(self._g_ptrs), ptr(self._state), stream_ptr()), launches=1)
+                check(L.up3d_grad_sumsq(*head, ptr(self._g_ptrs), float(self.grad_scale), ptr(self._state), stream_ptr()),
+                      launches=1)
                 ev[1].record()
                 check(L.up3d_adamw_apply(*head, ptr(self._p_ptrs), ptr(self._g_ptrs), ptr(self._m_ptrs), ptr(self._v_ptrs),
                                          ptr(self._s_ptrs), ptr(self._group), ptr(self._lrs), float(g0["betas"][0]),
                                          float(g0["betas"][1]), float(g0["eps"]), float(g0["weight_decay"]), self.max_norm,
-                                         ptr(self._state), stream_ptr()), launches=1)
+                                         float(self.grad_scale), ptr(self._state), stream_ptr()), launches=1)
                 ev[2].record()
                 torch.cuda.synchronize()
                 t_sq += ev[0].elapsed_time(ev[1])
