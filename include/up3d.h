@@ -182,6 +182,14 @@ UP3D_API int up3d_raster_timing_read(float *ms6);
 UP3D_API int up3d_focal_l2_loss(int64_t n_images, int H, int W, const float *rendered, const float *gt, const float *bg,
                        float non_bg_rate, float bg_rate, float *loss_out, float *dL_drendered,
                        up3d_stream_t stream);
+/* Same, with gt read in place: gt_is_u8 != 0 -> gt holds the 8-bit images as decoded from the dataset (value/255 is
+ * applied per read, the division the reference's loader does on the host); image n = (object n / views_per_object,
+ * view n % views_per_object) starts at gt + object*gt_object_stride + view*3*H*W elements -- the trainer's
+ * gt_images[:, input_images:] slice (train_network.py:427,444) without a copy. */
+UP3D_API int up3d_focal_l2_loss_strided(int64_t n_images, int H, int W, const float *rendered, const void *gt, int gt_is_u8,
+                                        int64_t views_per_object, int64_t gt_object_stride, const float *bg,
+                                        float non_bg_rate, float bg_rate, float *loss_out, float *dL_drendered,
+                                        up3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Transformer-encoder glue (openpoints/models/backbone/transformer.py:89-121 Block, 123-207

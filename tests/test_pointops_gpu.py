@@ -134,3 +134,25 @@ def test_focal_l2_loss_kernel_matches_torch_formula():
         l2.backward()
         assert abs(float(l1) - float(l2)) <= 1e-6 * max(1.0, abs(float(l2)))
         assert float((g1 - r.grad).abs().max()) <= 1e-9 + 1e-6 * float(r.grad.abs().max())
+
+
+def test_focal_l2_reads_uint8_view_in_place():
+    """The fused loss on a (B,V',3,H,W) view-axis slice of 8-bit images == the float formula on slice/255."""
+    import torch
+    from unipre3d_b200.loss import focal_l2_loss, focal_l2_loss_torch
+    torch.manual_seed(0)
+    B, V, H, W = 3, 5, 24, 20
+    gt8 = torch.randint(0, 256, (B, V, 3, H, W), dtype=torch.uint8, device="cuda")
+    gt8[:, :, :, :7] = 0                                   # background rows (black)
+    r = torch.rand(B * (V - 1), 3, H, W, device="cuda", requires_grad=True)
+    bg = torch.zeros(3, device="cuda")
+    view = gt8[:, 1:]
+    l1 = focal_l2_loss(r, view, bg, 4, 1)
+    (g1,) = torch.autograd.grad(l1, r)
+    gtf = (view.float() / 255.0).reshape(-1, 3, H, W)
+    l2 = focal_l2_loss_torch(r, gtf, bg, 4, 1)
+    (g2,) = torch.autograd.grad(l2, r)
+    assert abs(float(l1) - float(l2)) <= 1e-6 * abs(float(l2))
+    assert torch.allclose(g1, g2, atol=1e-9, rtol=1e-5)
+    l3 = focal_l2_loss(r, (gt8.float() / 255.0)[:, 1:], bg, 4, 1)       # float view, also in place
+    assert abs(float(l3) - float(l2)) <= 1e-6 * abs(float(l2))

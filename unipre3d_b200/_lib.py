@@ -49,6 +49,7 @@ def _load() -> C.CDLL:
         "up3d_raster_debug_state": (i32, [D] + [vp] * 11),
         "up3d_raster_debug_tile_lists": (i32, [D] + [vp] * 5),
         "up3d_focal_l2_loss": (i32, [i64, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp]),
+        "up3d_focal_l2_loss_strided": (i32, [i64, i32, i32, vp, vp, i32, i64, i64, vp, f32, f32, vp, vp, vp]),
         "up3d_raster_timing_enable": (i32, [i32]),
         "up3d_raster_timing_read": (i32, [C.POINTER(C.c_float)]),
         "up3d_ln_fwd": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp]),
@@ -93,6 +94,7 @@ EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_residen
             "up3d_group_points", "up3d_group_points_grad", "up3d_gather_points", "up3d_gather_points_grad",
             "up3d_subsample_group", "up3d_knn", "up3d_raster_state_bytes", "up3d_raster_scratch_bytes", "up3d_raster_forward",
             "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_focal_l2_loss",
+            "up3d_focal_l2_loss_strided",
             "up3d_raster_timing_enable", "up3d_raster_timing_read", "up3d_ln_fwd", "up3d_ln_bwd", "up3d_gelu_fwd",
             "up3d_gelu_bwd", "up3d_scale_cast_colsum", "up3d_adamw_chunk_elems", "up3d_adamw_step", "up3d_adamw_apply",
             "up3d_grad_sumsq", "up3d_stem_group_stats", "up3d_pn_conv1_stats", "up3d_pn_stats_tile_rows",

@@ -27,18 +27,36 @@ def focal_l2_loss_torch(network_output, gt, bg_color, non_bg_color_loss_rate, bg
     return (base_loss * weights).mean()
 
 
+def _gt_layout(gt):
+    """(base tensor for the pointer, is_u8, views_per_object, object stride in elements) of a gt that is either
+    (n,3,H,W) contiguous or a (B,V',3,H,W) slice of a contiguous (B,V,3,H,W) tensor along the view axis."""
+    if gt.dim() == 4:
+        g = gt.contiguous()
+        return g, g, int(g.shape[0]) or 1, 0
+    B, V, C, H, W = gt.shape
+    st = gt.stride()
+    if not (st[4] == 1 and st[3] == W and st[2] == H * W and st[1] == C * H * W):
+        g = gt.contiguous()
+        return g, g, V, V * C * H * W
+    return gt, gt, V, int(st[0])
+
+
 class _FocalL2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rendered, gt, bg, non_bg_rate, bg_rate):
         require_cuda(rendered, gt, bg)
-        rendered, gt, bg = rendered.contiguous().float(), gt.contiguous().float(), bg.contiguous().float()
+        rendered, bg = rendered.contiguous().float(), bg.contiguous().float()
         n, c, H, W = rendered.shape
-        assert c == 3 and gt.shape == rendered.shape
+        if gt.dtype not in (torch.uint8, torch.float32):
+            gt = gt.float()
+        keep, g, vpo, ostride = _gt_layout(gt)
+        assert c == 3 and gt.numel() == rendered.numel(), "gt and rendered images differ in size"
         out = torch.empty(4, dtype=torch.float32, device=rendered.device)
         dL = torch.empty_like(rendered)
         with torch.cuda.device(rendered.device):
-            check(_lib.lib.up3d_focal_l2_loss(n, H, W, ptr(rendered), ptr(gt), ptr(bg), float(non_bg_rate),
-                                              float(bg_rate), ptr(out), ptr(dL), stream_ptr()), launches=2)
+            check(_lib.lib.up3d_focal_l2_loss_strided(n, H, W, ptr(rendered), ptr(g), int(g.dtype == torch.uint8), vpo, ostride,
+                                                      ptr(bg), float(non_bg_rate), float(bg_rate), ptr(out), ptr(dL),
+                                                      stream_ptr()), launches=2)
         ctx.save_for_backward(dL)
         return out[0]
 
@@ -49,5 +67,7 @@ class _FocalL2(torch.autograd.Function):
 
 
 def focal_l2_loss(network_output, gt, bg_color, non_bg_color_loss_rate, bg_color_loss_rate):
-    """focal_l2_loss(rendered (n,3,H,W), gt, bg (3,), 4, 1) -> scalar; value and gradient from one fused kernel."""
+    """focal_l2_loss(rendered (n,3,H,W), gt, bg (3,), 4, 1) -> scalar; value and gradient from one fused kernel.
+    gt: (n,3,H,W) float32, or -- read in place, no copy -- a (B,V',3,H,W) view-axis slice of the batch's gt_images,
+    float32 or uint8 (8-bit images are divided by 255 per read)."""
     return _FocalL2.apply(network_output, gt, bg_color, non_bg_color_loss_rate, bg_color_loss_rate)

@@ -16,6 +16,7 @@ What changes relative to the reference loop (same math, fewer host round trips):
 from __future__ import annotations
 
 import copy
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -41,7 +42,12 @@ def prepare_model_inputs(data, cfg, bs_per_gpu, device):
               "source_cameras_view_to_world": data["view_to_world_transforms"][:, : cfg.data.input_images, ...],
               "image": None, "unprojected_coords": None}
     if cfg.opt.use_fusion:
-        inputs["image"] = data["gt_images"][:, : cfg.data.input_images, ...]
+        img = data["gt_images"][:, : cfg.data.input_images, ...]
+        if img.dtype == torch.uint8:
+            # 8-bit images as decoded from the dataset's PNGs: /255 on the device (the reference's loader divides on the
+            # host, dataset/shapenet.py); only the source views are converted -- the loss reads the 8-bit targets in place
+            img = img.to(device).float().div_(255.0)
+        inputs["image"] = img
     return _to_device(inputs, device)
 
 
@@ -220,21 +226,14 @@ class Trainer:
         out = render_batch_predicted(gaussian_splats, data["world_view_transforms"], data["full_proj_transforms"],
                                      data["camera_centers"], bg, self.cfg, view_slice=sl)
         rendered = out["render"]
-        gt = data["gt_images"][:, sl]
-        return rendered.reshape(-1, *rendered.shape[2:]), gt.reshape(-1, *gt.shape[2:])
-
-    @staticmethod
-    def _decode_images(data):
-        """8-bit images (as decoded from the dataset's PNGs) are divided by 255 on the device: the host->device copy
-        moves a quarter of the bytes of the float images the reference's loader produces on the host."""
-        if data["gt_images"].dtype == torch.uint8:
-            data = dict(data)
-            data["gt_images"] = data["gt_images"].to(torch.float32).div_(255.0)
-        return data
+        gt = data["gt_images"][:, sl]          # (B,V',3,H,W) view, float32 or uint8: the fused loss reads it in place
+        if self.cfg.opt.loss != "focal_l2":
+            gt = gt.reshape(-1, *gt.shape[2:])
+            gt = gt.float().div(255.0) if gt.dtype == torch.uint8 else gt
+        return rendered.reshape(-1, *rendered.shape[2:]), gt
 
     def _forward_backward(self, data) -> torch.Tensor:
         mm = self.model_manager
-        data = self._decode_images(data)
         model_inputs = prepare_model_inputs(data, self.cfg, self.bs_per_gpu, self.device)
         mm.forward_model.train()
         if self.autocast_dtype is not None:
@@ -279,7 +278,7 @@ class Trainer:
         self._comm_stream = torch.cuda.Stream(device=self.device)
         self._grad_pg = dist.new_group() if early else None       # second NCCL communicator: runs beside SyncBatchNorm's
         self.model_manager.optimizer.grad_scale = 1.0 / self.world
-        if early:
+        if early and not os.environ.get("UP3D_NO_EARLY_SYNC"):
             fused_encoder.GRAD_READY_HOOK = self._early_grad_hook
 
     def _early_views(self):
@@ -297,7 +296,7 @@ class Trainer:
         with torch.cuda.stream(self._comm_stream):
             dist.all_reduce(self._flat_early, op=dist.ReduceOp.SUM, group=self._grad_pg)
         self._early_pending = True
-        return self._early_views()          # fresh view objects: autograd can adopt them without a copy
+        return grads                        # autograd adopts the originals (no copy); _allreduce_grads re-points p.grad
 
     def _allreduce_grads(self) -> None:
         """N > 1: SUM the gradients over ranks (the optimizer applies 1/world) -- the stack's part was started by
