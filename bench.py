@@ -338,6 +338,19 @@ def ours(args):
         ms_e2e = timed(lambda i: losses.append(trainer.train_iteration(
             batches[i % n_batches], read_loss="lagged", prefetch=batches[(i + 1) % n_batches])))
         losses = [x for x in losses if x is not None] + [trainer.last_loss()]
+        # steady state without the artificial L2 flush (the step's own working set -- parameters, moments, gradients,
+        # shadows: ~520 MB -- already exceeds the 126 MB L2 several times over); reported next to the flushed headline
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step_resident(i)
+        e1.record()
+        barrier()
+        t_nf = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t_nf, op=dist.ReduceOp.MAX)
+        ms_noflush = float(t_nf.item()) / args.steps
     clocks = clk.summary()
     # kernels of libunipre3d_b200 per step (FPS, subsample_group, project, depth_sort, blend_forward, focal_l2 x2,
     # blend_backward, geometry_backward), counted from the C-ABI calls of one eager step; a graph replay launches
@@ -403,7 +416,10 @@ def ours(args):
                 "e2e": {"value": e2e, "unit": "views/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d * n_gpus, "d2h_bytes_per_step": 4 * n_gpus,
                         "last_loss": losses[-1] if losses else None},
-                "gpu_launches": gpu_launches, "cpu_baseline": cpu_baseline}
+                "gpu_launches": gpu_launches, "cpu_baseline": cpu_baseline,
+                "steady_state_no_l2_flush": {"ms_per_step": ms_noflush, "views_per_s": views_per_step / (ms_noflush * 1e-3),
+                                             "note": "same graph replays back to back, no flush between steps (not the "
+                                                     "headline; the flushed number above is)"}}
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:

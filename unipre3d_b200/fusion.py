@@ -28,6 +28,25 @@ class LazyImageFeatures:
         self.gn, self.conv = image_conv[0], image_conv[1]   # .shape / .dense() / .group_stats(G) / .gather(b, ix, iy)
         self.shape = (decoder_features.shape[0], self.conv.out_channels, *decoder_features.shape[2:])
 
+    def prefetch_stats(self) -> None:
+        """Analytic field on CUDA: start the GroupNorm-statistics kernel now, on the side stream, so it runs beside the
+        tokenizer's farthest-point sampling (64 busy SMs, ~100 us) instead of after the transformer."""
+        if torch.is_tensor(self.x) or not self.x.image.is_cuda or FORCE_MODULE_PATH:
+            return
+        from .fused_encoder import SideStream
+        self._side = SideStream(self.x.image.device)
+        self._sums = self._side.run(lambda img: self.x.group_sums(self.gn.num_groups), self.x.image)
+
+    def take_stats(self):
+        """-> sums (n,G,2) fp64, joined with the current stream."""
+        side = getattr(self, "_side", None)
+        if side is not None:
+            side.join()
+            self._side = None
+        elif getattr(self, "_sums", None) is None:
+            self._sums = self.x.group_sums(self.gn.num_groups)
+        return self._sums
+
     def dense(self) -> torch.Tensor:
         x = self.x if torch.is_tensor(self.x) else self.x.dense()
         return self.conv(self.gn(x))
@@ -42,7 +61,7 @@ class LazyImageFeatures:
                 var, mean = torch.var_mean(x.reshape(n, G, -1).float(), dim=2, unbiased=False)      # (n,G)
                 xs = x[bidx, :, ix, iy].float()                                                      # (B,N,Cin)
             else:
-                mean, var = x.group_stats(G)
+                mean, var = x.stats_from_sums(self.take_stats(), G)
                 xs = x.gather(bidx, ix, iy)
             rstd = torch.rsqrt(var + gn.eps)
             cpg = Cin // G
@@ -70,7 +89,7 @@ def fused_project_and_sample(lazy: "LazyImageFeatures", center, c2w_matrix, intr
     dev = center.device
     with torch.no_grad(), torch.autocast("cuda", enabled=False):
         w2c = torch.linalg.inv_ex(c2w_matrix.permute(0, 2, 1).float()).inverse.contiguous()
-        sums = field.group_sums(G)
+        sums = lazy.take_stats()
         keep = torch.empty((B, N), dtype=torch.uint8, device=dev)
         pix = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
         xhat = torch.empty((B, N, Cin), dtype=torch.float32, device=dev)

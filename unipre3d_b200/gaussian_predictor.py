@@ -66,8 +66,11 @@ class StemFeatureField:
     @torch.no_grad()
     def group_stats(self, num_groups: int):
         """-> (mean, biased var), each (n, G), over each group's channels x pixels (torch.var_mean(unbiased=False))."""
+        return self.stats_from_sums(self.group_sums(num_groups), num_groups)
+
+    @torch.no_grad()
+    def stats_from_sums(self, sums: torch.Tensor, num_groups: int):
         n, Cc, H, W = self.shape
-        sums = self.group_sums(num_groups)
         cnt = float((Cc // num_groups) * H * W)
         mean = sums[..., 0] / cnt
         var = (sums[..., 1] / cnt - mean * mean).clamp_min(0.0)
@@ -249,6 +252,7 @@ class GaussianSplatPredictor(nn.Module):
         else:
             image_output = self.image_network.forward(image, lazy=True)
             image_features = LazyImageFeatures(image_output["decoder_block_3"], self.image_conv)
+            image_features.prefetch_stats()
         point_features, center = self.point_network.forward_feat_fusion(
             point_cloud, image_features, source_cameras_view_to_world, self.fusion_mlps, self.intrinsic)
         if point_features.is_cuda and not getattr(self, "force_module_path", False):
