@@ -19,6 +19,7 @@
 // Every output row is owned by exactly one CTA: no atomics, deterministic.
 #include <cuda_bf16.h>
 #include <mma.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -333,6 +334,17 @@ attn_bwd_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const b
 
 }  // namespace up3d
 
+namespace up3d {
+// register-resident mma.sync variant (attention_mma.cu): the default; UP3D_ATTN_WMMA=1 selects the kernels above
+int attn_fwd_mma_launch(int B, int L, int H, float scale, const void *qkv, void *o, float *lse, cudaStream_t st);
+int attn_bwd_mma_launch(int B, int L, int H, float scale, const void *qkv, const void *o, const float *lse, const void *dout,
+                        void *dqkv, cudaStream_t st);
+static bool attn_use_mma() {
+    static const bool v = []() { const char *e = getenv("UP3D_ATTN_WMMA"); return !(e && e[0] == '1'); }();
+    return v;
+}
+}  // namespace up3d
+
 using namespace up3d;
 
 extern "C" int up3d_attn_max_len(void) { return AT_MAX_L; }
@@ -350,6 +362,7 @@ extern "C" int up3d_attn_fwd(int B, int L, int H, int D, float scale, const void
     if (B == 0) return 0;
     UP3D_CHECK_ARG(qkv && o && lse, "up3d_attn_fwd: NULL pointer");
     UP3D_CHECK_ARG(((((uintptr_t)qkv) | ((uintptr_t)o)) & 15) == 0, "up3d_attn_fwd: pointers must be 16-byte aligned");
+    if (attn_use_mma()) return attn_fwd_mma_launch(B, L, H, scale, qkv, o, lse, (cudaStream_t)stream);
     const AttnSmemFwd lay(at_round16(L));
     static size_t configured = 0;
     if (lay.total > configured) {
@@ -369,6 +382,7 @@ extern "C" int up3d_attn_bwd(int B, int L, int H, int D, float scale, const void
     UP3D_CHECK_ARG(qkv && o && lse && dout && dqkv, "up3d_attn_bwd: NULL pointer");
     UP3D_CHECK_ARG(((((uintptr_t)qkv) | ((uintptr_t)o) | ((uintptr_t)dout) | ((uintptr_t)dqkv)) & 15) == 0,
                    "up3d_attn_bwd: pointers must be 16-byte aligned");
+    if (attn_use_mma()) return attn_bwd_mma_launch(B, L, H, scale, qkv, o, lse, dout, dqkv, (cudaStream_t)stream);
     const AttnSmemBwd lay(at_round16(L), at_rows(L));
     static size_t configured = 0;
     if (lay.total > configured) {

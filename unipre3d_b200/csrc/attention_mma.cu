@@ -1,0 +1,306 @@
+// attention_mma.cu -- register-resident variant of the attention kernels of attention.cu (same entry-point contract,
+// same tiling: one CTA per (48-row tile, head, sample), whole K/V (+Q/dO) of the (sample, head) in shared memory).
+//
+// The first version staged S = QK^T, P and dS through shared memory between two warp-level-MMA GEMMs (9 block-wide
+// barriers, 166 KB of shared memory, issue slots 40 % busy).  Here the score tile never leaves registers: with
+// mma.sync.m16n8k16 the fp32 accumulators of two adjacent 16x8 score tiles ARE, after packing to bf16, the A fragment of
+// the next GEMM's k16 step, so softmax / dS are computed on the accumulators and fed straight back to the tensor core.
+//   forward : per warp 16 query rows, online softmax over 16-key chunks, O accumulated in registers (3 warps / CTA)
+//   backward: warps 0-2 = role A (queries of the tile -> dQ), warps 3-5 = role B (keys of the tile -> dK, dV, the
+//             transposed problem), each streaming 16-row chunks of the other side; no barrier after the operand load.
+// Operands are loaded with cp.async and read with ldmatrix (row stride 144 B: conflict-free); zero padding of the rows
+// past L makes every masked product vanish, so only the forward's softmax needs an explicit key mask.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace up3d {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int AM_D = 64, AM_QT = 48, AM_LD = 72, AM_MAX_L = 192;
+constexpr int AM_FWD_THREADS = 96, AM_BWD_THREADS = 192;
+
+__host__ __device__ inline int am_round16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline int am_rows(int L) { const int a = am_round16(L), b = (L + AM_QT - 1) / AM_QT * AM_QT; return a > b ? a : b; }
+__host__ __device__ inline size_t am_align128(size_t x) { return (x + 127) & ~(size_t)127; }
+
+__device__ __forceinline__ void am_load_rows(bf16 *dst, const bf16 *src, size_t row_stride, int row0, int n_valid, int n_rows) {
+    for (int i = threadIdx.x; i < n_rows * 8; i += blockDim.x) {
+        const int r = i >> 3, ch = i & 7;
+        const bool ok = r < n_valid;
+        const bf16 *g = ok ? src + (size_t)(row0 + r) * row_stride + ch * 8 : src;
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + r * AM_LD + ch * 8);
+        const int nbytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(g), "r"(nbytes) : "memory");
+    }
+}
+__device__ __forceinline__ void am_async_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], const bf16 *p) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(unsigned (&r)[4], const bf16 *p) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+// D(16x8, fp32) += A(16x16 bf16, row) * B(16x8 bf16, col)
+__device__ __forceinline__ void mma16816(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned *>(&v);
+}
+
+// A fragments (4 k16 steps over the 64-wide rows) of the 16 rows starting at `row0` of Xs [.][AM_LD]
+__device__ __forceinline__ void am_load_a(unsigned (&a)[4][4], const bf16 *Xs, int row0, int lane) {
+    const bf16 *p = Xs + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * AM_LD + (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(a[ks], p + ks * 16);
+}
+// (16 x 16) = A(16 x 64) * Y[n0 .. n0+15][:]^T : c0 = columns n0..n0+7, c1 = columns n0+8..n0+15
+__device__ __forceinline__ void am_xyT_chunk(float (&c0)[4], float (&c1)[4], const unsigned (&a)[4][4], const bf16 *Ys, int n0,
+                                             int lane) {
+    const bf16 *p = Ys + (n0 + (lane & 7) + (lane >> 4) * 8) * AM_LD + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        unsigned b[4];
+        ldsm_x4(b, p + ks * 16);
+        mma16816(c0, a[ks], b[0], b[1]);
+        mma16816(c1, a[ks], b[2], b[3]);
+    }
+}
+// acc(16 x 64) += P(16 x 16, A fragment) * Y[k0 .. k0+15][0..63]
+__device__ __forceinline__ void am_py_chunk(float (&acc)[8][4], const unsigned (&pa)[4], const bf16 *Ys, int k0, int lane) {
+    const bf16 *p = Ys + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * AM_LD + (lane >> 4) * 8;
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+        unsigned b[4];
+        ldsm_x4_trans(b, p + np * 16);
+        mma16816(acc[2 * np], pa, b[0], b[1]);
+        mma16816(acc[2 * np + 1], pa, b[2], b[3]);
+    }
+}
+// 16 x 64 fp32 accumulators -> bf16 rows [row0 + g], [row0 + g + 8] of a (T, row_stride) matrix
+__device__ __forceinline__ void am_store_acc(bf16 *dst, size_t row_stride, int row0, int n_valid, const float (&acc)[8][4],
+                                             float s_lo, float s_hi, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (g < n_valid)
+            *reinterpret_cast<__nv_bfloat162 *>(dst + (size_t)(row0 + g) * row_stride + 8 * j + 2 * t) =
+                __floats2bfloat162_rn(acc[j][0] * s_lo, acc[j][1] * s_lo);
+        if (g + 8 < n_valid)
+            *reinterpret_cast<__nv_bfloat162 *>(dst + (size_t)(row0 + g + 8) * row_stride + 8 * j + 2 * t) =
+                __floats2bfloat162_rn(acc[j][2] * s_hi, acc[j][3] * s_hi);
+    }
+}
+
+__global__ void __launch_bounds__(AM_FWD_THREADS)
+attn_fwd_mma_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, bf16 *__restrict__ o, float *__restrict__ lse) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Lp = am_round16(L), C = H * AM_D;
+    bf16 *Ks = reinterpret_cast<bf16 *>(smem);
+    bf16 *Vs = reinterpret_cast<bf16 *>(smem + am_align128((size_t)Lp * AM_LD * 2));
+    bf16 *Qs = reinterpret_cast<bf16 *>(smem + 2 * am_align128((size_t)Lp * AM_LD * 2));
+    const int t0 = blockIdx.x * AM_QT, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const size_t rs = (size_t)3 * C;
+    const bf16 *base = qkv + (size_t)b * L * rs + h * AM_D;
+    const int n_q = min(AM_QT, L - t0);
+    am_load_rows(Ks, base + C, rs, 0, L, Lp);
+    am_load_rows(Vs, base + 2 * C, rs, 0, L, Lp);
+    am_load_rows(Qs, base, rs, t0, n_q, AM_QT);
+    am_async_wait();
+    __syncthreads();
+
+    unsigned qa[4][4];
+    am_load_a(qa, Qs, warp * 16, lane);
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;      // rows g and g+8 (l: this lane's partial sum)
+    for (int n0 = 0; n0 < Lp; n0 += 16) {
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        am_xyT_chunk(s0, s1, qa, Ks, n0, lane);
+        const int c = n0 + 2 * t;                                          // columns c, c+1 (s0) and c+8, c+9 (s1)
+        const float v00 = c < L ? s0[0] * scale : -INFINITY, v01 = c + 1 < L ? s0[1] * scale : -INFINITY;
+        const float v02 = c + 8 < L ? s1[0] * scale : -INFINITY, v03 = c + 9 < L ? s1[1] * scale : -INFINITY;
+        const float v10 = c < L ? s0[2] * scale : -INFINITY, v11 = c + 1 < L ? s0[3] * scale : -INFINITY;
+        const float v12 = c + 8 < L ? s1[2] * scale : -INFINITY, v13 = c + 9 < L ? s1[3] * scale : -INFINITY;
+        float mx_lo = fmaxf(fmaxf(v00, v01), fmaxf(v02, v03)), mx_hi = fmaxf(fmaxf(v10, v11), fmaxf(v12, v13));
+        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+        const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);   // finite: every chunk holds a valid key
+        const float al_lo = __expf(m_lo - mn_lo), al_hi = __expf(m_hi - mn_hi);
+        const float p00 = __expf(v00 - mn_lo), p01 = __expf(v01 - mn_lo), p02 = __expf(v02 - mn_lo), p03 = __expf(v03 - mn_lo);
+        const float p10 = __expf(v10 - mn_hi), p11 = __expf(v11 - mn_hi), p12 = __expf(v12 - mn_hi), p13 = __expf(v13 - mn_hi);
+        l_lo = l_lo * al_lo + (p00 + p01) + (p02 + p03);
+        l_hi = l_hi * al_hi + (p10 + p11) + (p12 + p13);
+        m_lo = mn_lo; m_hi = mn_hi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j][0] *= al_lo; acc[j][1] *= al_lo; acc[j][2] *= al_hi; acc[j][3] *= al_hi; }
+        const unsigned pa[4] = {pack_bf16(p00, p01), pack_bf16(p10, p11), pack_bf16(p02, p03), pack_bf16(p12, p13)};
+        am_py_chunk(acc, pa, Vs, n0, lane);
+    }
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    const int r0 = warp * 16, nv = n_q - r0;                               // valid rows of this warp's strip
+    am_store_acc(o + (size_t)b * L * C + h * AM_D, C, t0 + r0, nv, acc, 1.f / l_lo, 1.f / l_hi, lane);
+    if (t == 0) {
+        float *lrow = lse + ((size_t)b * H + h) * L + t0 + r0;
+        if (g < nv) lrow[g] = m_lo + __logf(l_lo);
+        if (g + 8 < nv) lrow[g + 8] = m_hi + __logf(l_hi);
+    }
+}
+
+__global__ void __launch_bounds__(AM_BWD_THREADS)
+attn_bwd_mma_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const bf16 *__restrict__ o,
+                    const float *__restrict__ lse, const bf16 *__restrict__ dout, bf16 *__restrict__ dqkv) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Lp = am_round16(L), Lr = am_rows(L), C = H * AM_D;
+    const size_t tile = am_align128((size_t)Lr * AM_LD * 2);
+    bf16 *Qs = reinterpret_cast<bf16 *>(smem), *Ks = reinterpret_cast<bf16 *>(smem + tile);
+    bf16 *Vs = reinterpret_cast<bf16 *>(smem + 2 * tile), *dOs = reinterpret_cast<bf16 *>(smem + 3 * tile);
+    float *lse_s = reinterpret_cast<float *>(smem + 4 * tile), *delta_s = lse_s + Lr;
+    const int t0 = blockIdx.x * AM_QT, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const size_t rs = (size_t)3 * C;
+    const bf16 *base = qkv + (size_t)b * L * rs + h * AM_D;
+    const bf16 *obase = o + (size_t)b * L * C + h * AM_D, *dobase = dout + (size_t)b * L * C + h * AM_D;
+    bf16 *dbase = dqkv + (size_t)b * L * rs + h * AM_D;
+    const int n_t = min(AM_QT, L - t0);
+
+    am_load_rows(Qs, base, rs, 0, L, Lr);
+    am_load_rows(Ks, base + C, rs, 0, L, Lr);
+    am_load_rows(Vs, base + 2 * C, rs, 0, L, Lr);
+    am_load_rows(dOs, dobase, C, 0, L, Lr);
+    for (int r = threadIdx.x; r < Lr; r += AM_BWD_THREADS) lse_s[r] = r < L ? lse[((size_t)b * H + h) * L + r] : 0.f;
+    {   // delta_i = sum_d dO[i][d] * O[i][d]: 8 threads per row, O straight from global
+        constexpr int NIT = (AM_MAX_L * 8 + AM_BWD_THREADS - 1) / AM_BWD_THREADS;
+        uint4 ov[NIT];
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {
+            const int i = threadIdx.x + j * AM_BWD_THREADS, r = i >> 3, ch = i & 7;
+            ov[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < Lr * 8 && r < L) ov[j] = *reinterpret_cast<const uint4 *>(obase + (size_t)r * C + ch * 8);
+        }
+        am_async_wait();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {
+            const int i = threadIdx.x + j * AM_BWD_THREADS, r = i >> 3, ch = i & 7;
+            float v = 0.f;
+            if (i < Lr * 8) {
+                const uint4 dv = *reinterpret_cast<const uint4 *>(dOs + r * AM_LD + ch * 8);
+                const __nv_bfloat162 *oh = reinterpret_cast<const __nv_bfloat162 *>(&ov[j]);
+                const __nv_bfloat162 *dh = reinterpret_cast<const __nv_bfloat162 *>(&dv);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 of = __bfloat1622float2(oh[k]), df = __bfloat1622float2(dh[k]);
+                    v = fmaf(of.x, df.x, fmaf(of.y, df.y, v));
+                }
+            }
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if (i < Lr * 8 && ch == 0) delta_s[r] = v;
+        }
+    }
+    __syncthreads();
+
+    float acc0[8][4], acc1[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc0[j][k] = acc1[j][k] = 0.f;
+
+    if (warp < 3) {
+        // ---------------- role A: 16 queries (rows r0..r0+15 of the tile) against all keys -> dQ
+        const int r0 = t0 + warp * 16;
+        unsigned qa[4][4], da[4][4];
+        am_load_a(qa, Qs, r0, lane);
+        am_load_a(da, dOs, r0, lane);
+        const float l_lo = lse_s[r0 + g], l_hi = lse_s[r0 + g + 8], d_lo = delta_s[r0 + g], d_hi = delta_s[r0 + g + 8];
+        for (int n0 = 0; n0 < Lp; n0 += 16) {
+            float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f};
+            am_xyT_chunk(s0, s1, qa, Ks, n0, lane);
+            am_xyT_chunk(p0, p1, da, Vs, n0, lane);
+            // dS = P o (dP - delta) * scale.  Keys >= L: K rows are zero, so their dS column multiplies zero rows of K below.
+            const float e00 = __expf(s0[0] * scale - l_lo) * (p0[0] - d_lo) * scale, e01 = __expf(s0[1] * scale - l_lo) * (p0[1] - d_lo) * scale;
+            const float e02 = __expf(s1[0] * scale - l_lo) * (p1[0] - d_lo) * scale, e03 = __expf(s1[1] * scale - l_lo) * (p1[1] - d_lo) * scale;
+            const float e10 = __expf(s0[2] * scale - l_hi) * (p0[2] - d_hi) * scale, e11 = __expf(s0[3] * scale - l_hi) * (p0[3] - d_hi) * scale;
+            const float e12 = __expf(s1[2] * scale - l_hi) * (p1[2] - d_hi) * scale, e13 = __expf(s1[3] * scale - l_hi) * (p1[3] - d_hi) * scale;
+            const unsigned dsa[4] = {pack_bf16(e00, e01), pack_bf16(e10, e11), pack_bf16(e02, e03), pack_bf16(e12, e13)};
+            am_py_chunk(acc0, dsa, Ks, n0, lane);
+        }
+        am_store_acc(dbase, rs, r0, n_t - warp * 16, acc0, 1.f, 1.f, lane);
+    } else {
+        // ---------------- role B: 16 keys (rows r0..r0+15 of the tile) against all queries -> dV (acc0), dK (acc1)
+        const int w = warp - 3, r0 = t0 + w * 16;
+        unsigned ka[4][4], va[4][4];
+        am_load_a(ka, Ks, r0, lane);
+        am_load_a(va, Vs, r0, lane);
+        for (int i0 = 0; i0 < Lp; i0 += 16) {
+            float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f};
+            am_xyT_chunk(s0, s1, ka, Qs, i0, lane);            // S^T[key][query]
+            am_xyT_chunk(p0, p1, va, dOs, i0, lane);           // dP^T[key][query]
+            const int c = i0 + 2 * t;                          // query columns c, c+1 (x0) and c+8, c+9 (x1)
+            const float2 la = *reinterpret_cast<const float2 *>(lse_s + c), lb = *reinterpret_cast<const float2 *>(lse_s + c + 8);
+            const float2 da_ = *reinterpret_cast<const float2 *>(delta_s + c), db_ = *reinterpret_cast<const float2 *>(delta_s + c + 8);
+            // queries >= L: Q and dO rows are zero and lse = delta = 0, so P = 1 meets dO = 0 and dS = 0 meets Q = 0
+            const float q00 = __expf(s0[0] * scale - la.x), q01 = __expf(s0[1] * scale - la.y);
+            const float q02 = __expf(s1[0] * scale - lb.x), q03 = __expf(s1[1] * scale - lb.y);
+            const float q10 = __expf(s0[2] * scale - la.x), q11 = __expf(s0[3] * scale - la.y);
+            const float q12 = __expf(s1[2] * scale - lb.x), q13 = __expf(s1[3] * scale - lb.y);
+            const unsigned pa[4] = {pack_bf16(q00, q01), pack_bf16(q10, q11), pack_bf16(q02, q03), pack_bf16(q12, q13)};
+            const unsigned dsa[4] = {pack_bf16(q00 * (p0[0] - da_.x) * scale, q01 * (p0[1] - da_.y) * scale),
+                                     pack_bf16(q10 * (p0[2] - da_.x) * scale, q11 * (p0[3] - da_.y) * scale),
+                                     pack_bf16(q02 * (p1[0] - db_.x) * scale, q03 * (p1[1] - db_.y) * scale),
+                                     pack_bf16(q12 * (p1[2] - db_.x) * scale, q13 * (p1[3] - db_.y) * scale)};
+            am_py_chunk(acc0, pa, dOs, i0, lane);              // dV += P^T dO
+            am_py_chunk(acc1, dsa, Qs, i0, lane);              // dK += dS^T Q
+        }
+        am_store_acc(dbase + 2 * C, rs, r0, n_t - w * 16, acc0, 1.f, 1.f, lane);
+        am_store_acc(dbase + C, rs, r0, n_t - w * 16, acc1, 1.f, 1.f, lane);
+    }
+}
+
+size_t am_fwd_smem(int L) { const int Lp = am_round16(L); return 2 * am_align128((size_t)Lp * AM_LD * 2) + am_align128((size_t)AM_QT * AM_LD * 2); }
+size_t am_bwd_smem(int L) { const int Lr = am_rows(L); return 4 * am_align128((size_t)Lr * AM_LD * 2) + am_align128((size_t)2 * Lr * 4); }
+
+int attn_fwd_mma_launch(int B, int L, int H, float scale, const void *qkv, void *o, float *lse, cudaStream_t st) {
+    const size_t sm = am_fwd_smem(L);
+    static size_t configured = 0;
+    if (sm > configured) {
+        UP3D_CUDA_OK(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        configured = sm;
+    }
+    attn_fwd_mma_kernel<<<dim3(div_up(L, AM_QT), H, B), AM_FWD_THREADS, sm, st>>>(L, H, scale, (const bf16 *)qkv, (bf16 *)o, lse);
+    UP3D_LAUNCH_OK("attn_fwd_mma_kernel");
+    return 0;
+}
+
+int attn_bwd_mma_launch(int B, int L, int H, float scale, const void *qkv, const void *o, const float *lse, const void *dout,
+                        void *dqkv, cudaStream_t st) {
+    const size_t sm = am_bwd_smem(L);
+    static size_t configured = 0;
+    if (sm > configured) {
+        UP3D_CUDA_OK(cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        configured = sm;
+    }
+    attn_bwd_mma_kernel<<<dim3(div_up(L, AM_QT), H, B), AM_BWD_THREADS, sm, st>>>(L, H, scale, (const bf16 *)qkv, (const bf16 *)o,
+                                                                                   lse, (const bf16 *)dout, (bf16 *)dqkv);
+    UP3D_LAUNCH_OK("attn_bwd_mma_kernel");
+    return 0;
+}
+
+}  // namespace up3d
