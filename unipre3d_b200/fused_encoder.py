@@ -7,7 +7,8 @@ Block is 8 launches forward and ~17 backward:
 
     forward   ln_fwd (residual + DropPath scale + pos + LayerNorm, one pass) -> qkv GEMM -> attention -> proj GEMM(+bias)
               -> ln_fwd -> fc1 GEMM(+bias) -> gelu_fwd -> fc2 GEMM(+bias)
-    backward  2 GEMMs per Linear (dX in the activation dtype, dW written in fp32 by the GEMM), gelu_bwd (+ fc1 bias
+    backward  1 dX GEMM per Linear; the weight gradients of each Linear for ALL blocks are one batched GEMM at the end
+              (their operands are written into (depth, T, .) stacks as they are produced), gelu_bwd (+ fc1 bias
               gradient), ln_bwd (+ residual add, LayerNorm parameter gradients, dpos accumulation, DropPath scale,
               cast and the bias gradient of the Linear in front -- all in the same pass), SDPA backward.
 
@@ -29,7 +30,7 @@ from . import _lib
 from ._lib import check, ptr, require_cuda, stream_ptr
 
 _KEEP_CACHE = {}
-SAVED_PER_BLOCK = 13    # xs, y1, mean1, rstd1, o, x2, y2, mean2, rstd2, pre, h, qkv, lse
+SAVED_PER_BLOCK = 9     # xs, mean1, rstd1, x2, mean2, rstd2, pre, qkv, lse  (+ the stacked Y1, O, Y2, H once)
 PARAMS_PER_BLOCK = 11   # norm1.w, norm1.b, qkv.w, proj.w, proj.b, norm2.w, norm2.b, fc1.w, fc1.b, fc2.w, fc2.b
 
 
@@ -37,11 +38,11 @@ def _flag(dtype) -> int:
     return 1 if dtype == torch.bfloat16 else 0
 
 
-def ln_fwd(x, delta, scale, pos, gamma, beta, eps, L, act_dtype, want_xs=True, want_y=True):
+def ln_fwd(x, delta, scale, pos, gamma, beta, eps, L, act_dtype, want_xs=True, want_y=True, y_out=None):
     """xs = x + scale[b]*delta + pos ; y = LN(xs).  x (T,C) fp32 -> (xs fp32 | None, y act | None, mean, rstd)."""
     T, C = x.shape
     xs = torch.empty_like(x) if want_xs else None
-    y = torch.empty((T, C), dtype=act_dtype, device=x.device) if want_y else None
+    y = (y_out if y_out is not None else torch.empty((T, C), dtype=act_dtype, device=x.device)) if want_y else None
     mean = torch.empty(T, dtype=torch.float32, device=x.device) if want_y else None
     rstd = torch.empty(T, dtype=torch.float32, device=x.device) if want_y else None
     check(_lib.lib.up3d_ln_fwd(_flag(act_dtype), T, L, C, ptr(x), ptr(delta), ptr(scale), ptr(pos), ptr(gamma), ptr(beta),
@@ -49,32 +50,33 @@ def ln_fwd(x, delta, scale, pos, gamma, beta, eps, L, act_dtype, want_xs=True, w
     return xs, y, mean, rstd
 
 
-def ln_bwd(dy, xs, mean, rstd, gamma, g_res, scale, L, dpos, want_scaled, dgamma, dbeta, dbias):
+def ln_bwd(dy, xs, mean, rstd, gamma, g_res, scale, L, dpos, want_scaled, dgamma, dbeta, dbias, scaled_out=None):
     T, C = xs.shape
     dx = torch.empty_like(xs)
-    dscaled = torch.empty((T, C), dtype=dy.dtype, device=xs.device) if want_scaled else None
+    dscaled = (scaled_out if scaled_out is not None else torch.empty((T, C), dtype=dy.dtype, device=xs.device)) \
+        if want_scaled else None
     check(_lib.lib.up3d_ln_bwd(_flag(dy.dtype), T, L, C, ptr(dy), ptr(xs), ptr(mean), ptr(rstd), ptr(gamma), ptr(g_res),
                                ptr(scale), ptr(dx), ptr(dpos), ptr(dscaled), ptr(dgamma), ptr(dbeta),
                                ptr(dbias if want_scaled else None), stream_ptr()), launches=1)
     return dx, dscaled
 
 
-def gelu_fwd(x):
-    y = torch.empty_like(x)
+def gelu_fwd(x, out=None):
+    y = out if out is not None else torch.empty_like(x)
     check(_lib.lib.up3d_gelu_fwd(_flag(x.dtype), x.numel(), ptr(x), ptr(y), stream_ptr()), launches=1)
     return y
 
 
-def gelu_bwd(dy, pre, dbias):
+def gelu_bwd(dy, pre, dbias, out=None):
     T, C = pre.shape
-    dx = torch.empty_like(pre)
+    dx = out if out is not None else torch.empty_like(pre)
     check(_lib.lib.up3d_gelu_bwd(_flag(pre.dtype), T, C, ptr(dy), ptr(pre), ptr(dx), ptr(dbias), stream_ptr()), launches=1)
     return dx
 
 
-def scale_cast_colsum(g, scale, L, act_dtype, dbias):
+def scale_cast_colsum(g, scale, L, act_dtype, dbias, out=None):
     T, C = g.shape
-    out = torch.empty((T, C), dtype=act_dtype, device=g.device)
+    out = out if out is not None else torch.empty((T, C), dtype=act_dtype, device=g.device)
     check(_lib.lib.up3d_scale_cast_colsum(_flag(act_dtype), T, L, C, ptr(g), ptr(scale), ptr(out), ptr(dbias),
                                           stream_ptr()), launches=1)
     return out
@@ -84,16 +86,16 @@ def attn_supported(act_dtype, L, D) -> bool:
     return act_dtype == torch.bfloat16 and D == 64 and L <= int(_lib.lib.up3d_attn_max_len())
 
 
-def attn_fwd(qkv, B, L, H, D, scale):
+def attn_fwd(qkv, B, L, H, D, scale, out=None):
     """qkv (B*L, 3*H*D) bf16 -> o (B*L, H*D) bf16, lse (B,H,L) fp32 (csrc/attention.cu)."""
-    o = torch.empty((B * L, H * D), dtype=qkv.dtype, device=qkv.device)
+    o = out if out is not None else torch.empty((B * L, H * D), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((B, H, L), dtype=torch.float32, device=qkv.device)
     check(_lib.lib.up3d_attn_fwd(B, L, H, D, float(scale), ptr(qkv), ptr(o), ptr(lse), stream_ptr()), launches=1)
     return o, lse
 
 
-def attn_bwd(qkv, o, lse, do, B, L, H, D, scale):
-    dqkv = torch.empty_like(qkv)
+def attn_bwd(qkv, o, lse, do, B, L, H, D, scale, out=None):
+    dqkv = out if out is not None else torch.empty_like(qkv)
     check(_lib.lib.up3d_attn_bwd(B, L, H, D, float(scale), ptr(qkv), ptr(o), ptr(lse), ptr(do), ptr(dqkv), stream_ptr()),
           launches=1)
     return dqkv
@@ -104,6 +106,14 @@ def _wgrad(dy, x):
     if dy.dtype == torch.float32:
         return dy.t() @ x
     return torch.mm(dy.t(), x, out_dtype=torch.float32)
+
+
+def _wgrad_batched(dy, x):
+    """(depth, T, out) x (depth, T, in) -> (depth, out, in) fp32: the weight gradients of one Linear of ALL blocks as a
+    single batched GEMM (16 launches of ~5 us become one)."""
+    if dy.dtype == torch.float32:
+        return torch.bmm(dy.transpose(1, 2), x)
+    return torch.bmm(dy.transpose(1, 2), x, out_dtype=torch.float32)
 
 
 _SIDE_STREAMS = {}
@@ -160,16 +170,21 @@ class EncoderStackFn(torch.autograd.Function):
         pend, pend_scale = None, None
         saved, attn_nodes = [], []
         own_attn = attn_supported(act, L, D)
+        Hd = meta.compute_weights[0][3].shape[0]
         with torch.cuda.device(x.device), torch.autocast("cuda", enabled=False):
+            # the A-side operands of the four weight-gradient GEMMs, stacked over the blocks (one batched GEMM each in
+            # the backward): LayerNorm outputs, attention outputs, GELU outputs
+            e = lambda n: torch.empty((depth, T, n), dtype=act, device=x.device)
+            Y1, O, Y2, HH = e(C), e(C), e(C), e(Hd)
             for i in range(depth):
                 n1w, n1b, _, _, _, n2w, n2b, _, _, _, _ = params[i * PARAMS_PER_BLOCK:(i + 1) * PARAMS_PER_BLOCK]
                 wqkv, wproj, bproj, w1, b1, w2, b2 = meta.compute_weights[i]
                 s1 = masks[2 * i] if masks is not None else None
                 s2 = masks[2 * i + 1] if masks is not None else None
-                xs, y1, mu1, rs1 = ln_fwd(xcur, pend, pend_scale, pos2, n1w, n1b, meta.eps1[i], L, act)
+                xs, y1, mu1, rs1 = ln_fwd(xcur, pend, pend_scale, pos2, n1w, n1b, meta.eps1[i], L, act, y_out=Y1[i])
                 qkv = y1 @ wqkv.t()
                 if own_attn:
-                    o, lse = attn_fwd(qkv, B, L, H, D, meta.scale)
+                    o, lse = attn_fwd(qkv, B, L, H, D, meta.scale, out=O[i])
                     attn_nodes.append(None)
                 else:                                   # fp32 operands (reference precision): library SDPA
                     with torch.enable_grad():
@@ -177,16 +192,17 @@ class EncoderStackFn(torch.autograd.Function):
                         q, k, v = qkv_l.view(B, L, 3, H, D).permute(2, 0, 3, 1, 4).unbind(0)
                         o4 = F.scaled_dot_product_attention(q, k, v, scale=meta.scale)
                         o_l = o4.transpose(1, 2).reshape(T, C)
-                    o, lse = o_l.detach(), mu1.new_empty(0)
+                    o, lse = O[i].copy_(o_l.detach()), mu1.new_empty(0)
                     attn_nodes.append((qkv_l, o_l))
                 a = F.linear(o, wproj, bproj)
-                x2, y2, mu2, rs2 = ln_fwd(xs, a, s1, None, n2w, n2b, meta.eps2[i], L, act)
+                x2, y2, mu2, rs2 = ln_fwd(xs, a, s1, None, n2w, n2b, meta.eps2[i], L, act, y_out=Y2[i])
                 pre = F.linear(y2, w1, b1)
-                h = gelu_fwd(pre)
+                h = gelu_fwd(pre, out=HH[i])
                 d = F.linear(h, w2, b2)
-                saved += [xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h, qkv, lse]
+                saved += [xs, mu1, rs1, x2, mu2, rs2, pre, qkv, lse]
                 xcur, pend, pend_scale = x2, d, s2
             out, _, _, _ = ln_fwd(xcur, pend, pend_scale, None, None, None, 0.0, L, act, want_y=False)
+        saved += [Y1, O, Y2, HH]
         ctx.meta, ctx.depth, ctx.attn_nodes, ctx.own_attn = meta, depth, attn_nodes, own_attn
         ctx.has_masks = masks is not None
         ctx.save_for_backward(*(saved + list(params) + ([masks] if masks is not None else [])))
@@ -198,8 +214,9 @@ class EncoderStackFn(torch.autograd.Function):
         B, L, C = meta.B, meta.L, meta.C
         T, act = B * L, meta.act_dtype
         sv = ctx.saved_tensors
-        n_act = SAVED_PER_BLOCK * depth
+        n_act = SAVED_PER_BLOCK * depth + 4
         H, D = meta.heads, C // meta.heads
+        Y1, O, Y2, HH = sv[n_act - 4:n_act]
         params = sv[n_act:n_act + PARAMS_PER_BLOCK * depth]
         masks = sv[-1] if ctx.has_masks else None
         Hd = meta.compute_weights[0][3].shape[0]
@@ -218,41 +235,43 @@ class EncoderStackFn(torch.autograd.Function):
 
             # slots: 0 n1w, 1 n1b, 2 bproj, 3 n2w, 4 n2b, 5 b2, 6.. b1
             s2_last = masks[2 * depth - 1] if masks is not None else None
-            side = SideStream(dev)
-            dd = scale_cast_colsum(g, s2_last, L, act, sm(depth - 1, 5))
+            # the dY operands of the four weight-gradient GEMMs, stacked over the blocks
+            e = lambda n: torch.empty((depth, T, n), dtype=act, device=dev)
+            DD, DPRE, DA, DQKV = e(C), e(Hd), e(C), e(3 * C)
+            dd = scale_cast_colsum(g, s2_last, L, act, sm(depth - 1, 5), out=DD[depth - 1])
             for i in range(depth - 1, -1, -1):
-                xs, y1, mu1, rs1, o, x2, y2, mu2, rs2, pre, h, qkv, lse = sv[SAVED_PER_BLOCK * i:SAVED_PER_BLOCK * (i + 1)]
+                xs, mu1, rs1, x2, mu2, rs2, pre, qkv, lse = sv[SAVED_PER_BLOCK * i:SAVED_PER_BLOCK * (i + 1)]
                 n1w, _, _, _, _, n2w, _, _, _, _, _ = params[i * PARAMS_PER_BLOCK:(i + 1) * PARAMS_PER_BLOCK]
                 wqkv, wproj, _, w1, _, w2, _ = meta.compute_weights[i]
                 s1 = masks[2 * i] if masks is not None else None
                 s2_prev = masks[2 * i - 1] if (masks is not None and i > 0) else None
                 # ---- MLP branch
                 dh = dd @ w2
-                gw2 = side.run(_wgrad, dd, h)
-                dpre = gelu_bwd(dh, pre, sm(i, 6, Hd))
+                dpre = gelu_bwd(dh, pre, sm(i, 6, Hd), out=DPRE[i])
                 dy2 = dpre @ w1
-                gw1 = side.run(_wgrad, dpre, y2)
-                dx2, da = ln_bwd(dy2, x2, mu2, rs2, n2w, g, s1, L, None, True, sm(i, 3), sm(i, 4), sm(i, 2))
+                dx2, da = ln_bwd(dy2, x2, mu2, rs2, n2w, g, s1, L, None, True, sm(i, 3), sm(i, 4), sm(i, 2),
+                                 scaled_out=DA[i])
                 # ---- attention branch
                 do = da @ wproj
-                gwproj = side.run(_wgrad, da, o)
                 if ctx.own_attn:
-                    dqkv = attn_bwd(qkv, o, lse, do, B, L, H, D, meta.scale)
+                    dqkv = attn_bwd(qkv, O[i], lse, do, B, L, H, D, meta.scale, out=DQKV[i])
                 else:
                     qkv_l, o_l = ctx.attn_nodes[i]
                     (dqkv,) = torch.autograd.grad(o_l, qkv_l, do)
-                    dqkv = dqkv.contiguous()
+                    dqkv = DQKV[i].copy_(dqkv)
                 dy1 = dqkv @ wqkv
-                gwqkv = side.run(_wgrad, dqkv, y1)
                 g, dd = ln_bwd(dy1, xs, mu1, rs1, n1w, dx2, s2_prev, L, dpos, i > 0, sm(i, 0), sm(i, 1),
-                               sm(i - 1, 5) if i > 0 else None)
+                               sm(i - 1, 5) if i > 0 else None, scaled_out=DD[i - 1] if i > 0 else None)
+            # ---- weight gradients of all blocks: four batched GEMMs (fp32 written by the GEMM)
+            gW2, gW1 = _wgrad_batched(DD, HH), _wgrad_batched(DPRE, Y2)
+            gWproj, gWqkv = _wgrad_batched(DA, O), _wgrad_batched(DQKV, Y1)
+            for i in range(depth):
                 base = i * PARAMS_PER_BLOCK
                 grads[base + 0], grads[base + 1] = sm(i, 0), sm(i, 1)
-                grads[base + 2], grads[base + 3], grads[base + 4] = gwqkv, gwproj, sm(i, 2)
+                grads[base + 2], grads[base + 3], grads[base + 4] = gWqkv[i], gWproj[i], sm(i, 2)
                 grads[base + 5], grads[base + 6] = sm(i, 3), sm(i, 4)
-                grads[base + 7], grads[base + 8] = gw1, sm(i, 6, Hd)
-                grads[base + 9], grads[base + 10] = gw2, sm(i, 5)
-            side.join()
+                grads[base + 7], grads[base + 8] = gW1[i], sm(i, 6, Hd)
+                grads[base + 9], grads[base + 10] = gW2[i], sm(i, 5)
             ctx.attn_nodes = None
             if GRAD_READY_HOOK is not None:
                 grads = GRAD_READY_HOOK(grads)
