@@ -17,6 +17,19 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+_ONES = {}
+
+
+def _ones_row(n: int, device) -> torch.Tensor:
+    key = (n, device)
+    t = _ONES.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            return torch.ones((1, n), dtype=torch.bfloat16, device=device)
+        t = _ONES[key] = torch.ones((1, n), dtype=torch.bfloat16, device=device)
+    return t
+
+
 class _ShadowLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, w16, b16):
@@ -39,7 +52,9 @@ class _ShadowLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = torch.mm(gy2.t(), x2, out_dtype=torch.float32)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy2.sum(0, dtype=torch.float32)
+            # column sum as a (1 x T) @ (T x out) GEMM with fp32 accumulation/output: same arithmetic as
+            # gy2.sum(0, dtype=float32) but ~4 us instead of torch's ~12 us strided bf16 reduction
+            gb = torch.mm(_ones_row(gy2.shape[0], gy2.device), gy2, out_dtype=torch.float32).reshape(-1)
         return gx, gw, gb, None, None
 
 
