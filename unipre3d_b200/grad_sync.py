@@ -1,0 +1,90 @@
+"""Gradient exchange of the data-parallel step (the reference wraps the model in DistributedDataParallel,
+/root/reference/pointcept/engines/defaults.py:22-43, train_network.py:183-186: bucketed all-reduce + division by world).
+
+`GradSync` keeps one flat fp32 buffer [early parameters | everything else]:
+
+  * `early_hook(grads)` -- called from INSIDE the backward (by the transformer stack's single backward node, whose
+    gradients are ~97 % of all gradient bytes and complete ~0.35 ms before the backward ends): packs them into the flat
+    buffer and starts their all-reduce on a second communicator (and, on CUDA, a second stream), so it overlaps the rest
+    of the backward instead of following it;
+  * `finish(params_with_grads)` -- after the backward: packs and all-reduces the remaining gradients, joins the early
+    all-reduce and points every `p.grad` at its slice of the flat buffer.
+
+Gradients are SUMMED; the 1/world of DDP's mean is applied by the optimizer (`FusedClipAdamW.grad_scale`), which saves a
+pass over the 118 MB buffer.  Device-agnostic: the same code runs over gloo on CPU tensors (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, params: Sequence[torch.nn.Parameter], early_params: Sequence[torch.nn.Parameter], device,
+                 overlap: bool = True):
+        self.world = dist.get_world_size()
+        self.device = torch.device(device)
+        early_ids = {id(p) for p in early_params}
+        self.early: List[torch.nn.Parameter] = list(early_params)
+        self.rest: List[torch.nn.Parameter] = [p for p in params if id(p) not in early_ids]
+        n_early, n_rest = sum(p.numel() for p in self.early), sum(p.numel() for p in self.rest)
+        self.flat = torch.zeros(n_early + n_rest, dtype=torch.float32, device=self.device)
+        self.flat_early, self.flat_rest = self.flat[:n_early], self.flat[n_early:]
+        self._early_slices, self._rest_views, off = [], [], 0
+        for p in self.early:
+            self._early_slices.append((off, off + p.numel(), tuple(p.shape)))
+            off += p.numel()
+        for p in self.rest:
+            self._rest_views.append(self.flat[off: off + p.numel()].view_as(p))
+            off += p.numel()
+        self.overlap = bool(overlap and self.early)
+        self._pending = None                       # "stream" (CUDA) or a dist.Work handle (CPU)
+        self.is_cuda = self.device.type == "cuda"
+        self._comm_stream = torch.cuda.Stream(device=self.device) if (self.is_cuda and self.overlap) else None
+        # second communicator: the early all-reduce must not queue behind (or in front of) the SyncBatchNorm collectives
+        # the rest of the backward issues on the default one
+        self._pg = dist.new_group() if self.overlap else None
+
+    def _early_views(self):
+        return [self.flat[a:b].view(shape) for a, b, shape in self._early_slices]
+
+    def _join(self) -> None:
+        if self._pending is None:
+            return
+        if self.is_cuda:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        else:
+            self._pending.wait()
+        self._pending = None
+
+    def early_hook(self, grads):
+        """grads: the early parameters' gradients, in `early_params` order.  Returns what autograd should see."""
+        if not self.overlap or len(grads) != len(self._early_slices):
+            return grads
+        self._join()                              # a previous backward that was never consumed (diagnostic passes)
+        torch._foreach_copy_(self._early_views(), list(grads))
+        if self.is_cuda:
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(self.flat_early, op=dist.ReduceOp.SUM, group=self._pg)
+            self._pending = "stream"
+        else:
+            self._pending = dist.all_reduce(self.flat_early, op=dist.ReduceOp.SUM, group=self._pg, async_op=True)
+        return grads                              # autograd adopts the originals (no copy); finish() re-points p.grad
+
+    def finish(self) -> None:
+        if any(p.grad is None for p in self.early + self.rest):
+            raise RuntimeError("a trainable parameter received no gradient (data-parallel ranks would diverge)")
+        if self._pending is None and self.early:  # the hook did not fire (module path / overlap off): reduce it now
+            torch._foreach_copy_(self._early_views(), [p.grad for p in self.early])
+            dist.all_reduce(self.flat_early, op=dist.ReduceOp.SUM)
+        if self.rest:
+            torch._foreach_copy_(self._rest_views, [p.grad for p in self.rest])
+            dist.all_reduce(self.flat_rest, op=dist.ReduceOp.SUM)
+        self._join()
+        for p, v in zip(self.early, self._early_views()):
+            p.grad = v
+        for p, v in zip(self.rest, self._rest_views):
+            p.grad = v

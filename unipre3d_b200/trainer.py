@@ -203,8 +203,7 @@ class Trainer:
             # the optimizer kernel rewrites the bf16 shadows together with the fp32 masters (no separate cast pass)
             self.model_manager.optimizer.set_shadows(
                 {id(m): s for m, s in zip(self._shadow.masters, self._shadow.shadows)})
-        self._flat_grad = None
-        self._early_pending = False
+        self._grad_sync = None
         if self.world > 1:
             self._setup_grad_sync()
         self.iteration = 0
@@ -249,76 +248,27 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------ data parallelism
     def _setup_grad_sync(self) -> None:
-        """Flat fp32 gradient buffer [transformer-stack parameters | everything else].  The stack's gradients (~97 % of
-        the bytes) are complete when its single backward node returns, ~0.35 ms before the end of the backward: their
-        all-reduce is started there, on a second communicator + stream, and overlaps the tokenizer's backward (whose
-        SyncBatchNorm collectives keep using the default communicator).  The 1/world factor is applied inside the
-        optimizer kernels (FusedClipAdamW.grad_scale)."""
+        """grad_sync.GradSync over [transformer-stack parameters | everything else]: the stack's gradients are all-reduced
+        from inside the backward (fused_encoder.GRAD_READY_HOOK), the rest after it; the 1/world factor is applied inside
+        the optimizer kernels (FusedClipAdamW.grad_scale)."""
         from . import fused_encoder
-        blocks = None
+        from .grad_sync import GradSync
         enc = getattr(getattr(self.model_manager.model, "point_network", None), "encoder", None)
         tb = getattr(getattr(enc, "blocks", None), "blocks", None)
-        if tb is not None and fused_encoder.supports(tb):
-            blocks = tb
-        early = fused_encoder.stack_parameters(blocks) if blocks is not None else []
-        early_ids = {id(p) for p in early}
-        rest = [p for p in self.params if id(p) not in early_ids]
-        n_early, n_rest = sum(p.numel() for p in early), sum(p.numel() for p in rest)
-        self._flat_grad = torch.zeros(n_early + n_rest, dtype=torch.float32, device=self.device)
-        self._flat_early, self._flat_rest = self._flat_grad[:n_early], self._flat_grad[n_early:]
-        self._early_params, self._rest_params = early, rest
-        self._early_slices, self._rest_views, off = [], [], 0
-        for p in early:
-            self._early_slices.append((off, off + p.numel(), tuple(p.shape)))
-            off += p.numel()
-        for p in rest:
-            self._rest_views.append(self._flat_grad[off: off + p.numel()].view_as(p))
-            off += p.numel()
-        self._early_pending = False
-        self._comm_stream = torch.cuda.Stream(device=self.device)
-        self._grad_pg = dist.new_group() if early else None       # second NCCL communicator: runs beside SyncBatchNorm's
+        early = fused_encoder.stack_parameters(tb) if (tb is not None and fused_encoder.supports(tb)) else []
+        self._grad_sync = GradSync(self.params, early, self.device, overlap=not os.environ.get("UP3D_NO_EARLY_SYNC"))
         self.model_manager.optimizer.grad_scale = 1.0 / self.world
-        if early and not os.environ.get("UP3D_NO_EARLY_SYNC"):
-            fused_encoder.GRAD_READY_HOOK = self._early_grad_hook
-
-    def _early_views(self):
-        return [self._flat_grad[a:b].view(shape) for a, b, shape in self._early_slices]
-
-    def _early_grad_hook(self, grads):
-        """Called by the transformer stack's backward node with its parameter gradients."""
-        if len(grads) != len(self._early_slices):
-            return grads
-        if self._early_pending:             # a previous backward was never consumed (diagnostic passes): serialise
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
-        views = self._early_views()
-        torch._foreach_copy_(views, [g for g in grads])
-        self._comm_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._comm_stream):
-            dist.all_reduce(self._flat_early, op=dist.ReduceOp.SUM, group=self._grad_pg)
-        self._early_pending = True
-        return grads                        # autograd adopts the originals (no copy); _allreduce_grads re-points p.grad
+        if self._grad_sync.overlap:
+            fused_encoder.GRAD_READY_HOOK = self._grad_sync.early_hook
 
     def _allreduce_grads(self) -> None:
-        """N > 1: SUM the gradients over ranks (the optimizer applies 1/world) -- the stack's part was started by
-        `_early_grad_hook` during the backward; the rest goes out now -- then point every p.grad at its flat slice."""
+        """N > 1: SUM the gradients over ranks (the optimizer applies 1/world) and point every p.grad at its slice of
+        the flat buffer."""
         if self.world == 1:
             return
-        if self._flat_grad is None:
+        if self._grad_sync is None:
             self._setup_grad_sync()
-        if any(p.grad is None for p in self.params):
-            raise RuntimeError("a trainable parameter received no gradient (data-parallel ranks would diverge)")
-        if not self._early_pending and self._early_params:      # the hook did not fire (module path): reduce everything now
-            torch._foreach_copy_(self._early_views(), [p.grad for p in self._early_params])
-            dist.all_reduce(self._flat_early, op=dist.ReduceOp.SUM)
-        torch._foreach_copy_(self._rest_views, [p.grad for p in self._rest_params])
-        dist.all_reduce(self._flat_rest, op=dist.ReduceOp.SUM)
-        if self._early_pending:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
-            self._early_pending = False
-        for p, v in zip(self._early_params, self._early_views()):
-            p.grad = v
-        for p, v in zip(self._rest_params, self._rest_views):
-            p.grad = v
+        self._grad_sync.finish()
 
     def _clip_and_step(self) -> None:
         """368-390 + 343-344 in two launches (optim.FusedClipAdamW): total norm on the device; non-finite -> the
