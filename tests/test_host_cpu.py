@@ -110,3 +110,57 @@ def test_cpu_port_step_runs_and_learns():
     d = synthetic.make_batch(cfg, 2, 512, seed=0)
     losses = [st.step(d) for _ in range(4)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+def test_uint8_batches_and_in_place_target_layout():
+    """Host-side pieces of the end-to-end path: 8-bit synthetic batches (a quarter of the H2D bytes, exact background
+    value) and the layout detection that lets the fused loss read gt_images[:, input_images:] without a copy."""
+    import torch
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.config import compose
+    from unipre3d_b200.loss import _gt_layout
+    cfg = compose(overrides=["data.training_resolution=32", "opt.batch_size=2"])
+    b8 = synthetic.make_batch(cfg, 2, 128, seed=3, image_dtype="uint8")
+    bf = synthetic.make_batch(cfg, 2, 128, seed=3)
+    assert b8["gt_images"].dtype == torch.uint8 and bf["gt_images"].dtype == torch.float32
+    assert b8["gt_images"].shape == bf["gt_images"].shape
+    assert int(b8["gt_images"].min()) == 0                      # black background stays exactly 0
+    assert synthetic.batch_nbytes(b8) < synthetic.batch_nbytes(bf)
+    gt = b8["gt_images"]
+    ni = int(cfg.data.input_images)
+    view = gt[:, ni:]
+    base, g, vpo, ostride = _gt_layout(view)
+    assert g.data_ptr() == view.data_ptr() and vpo == gt.shape[1] - ni and ostride == gt.stride(0)   # in place
+    flat = view.reshape(-1, *view.shape[2:])                    # the (n,3,H,W) form: contiguous copy, one "object"
+    _, g2, vpo2, ostride2 = _gt_layout(flat)
+    assert vpo2 == flat.shape[0] and ostride2 == 0
+    weird = gt.permute(0, 1, 2, 4, 3)[:, ni:]                   # not a view-axis slice of a contiguous tensor -> copied
+    _, g3, vpo3, ostride3 = _gt_layout(weird)
+    assert g3.is_contiguous() and ostride3 == weird.shape[1] * weird.shape[2] * weird.shape[3] * weird.shape[4]
+
+
+def test_fused_stack_parameter_order_and_support_predicate():
+    """fused_encoder.stack_parameters (the order gradients come back in, and the order GradSync packs them) covers
+    every Block parameter exactly once; supports() accepts the reference configuration and rejects what the kernels do
+    not implement."""
+    import torch
+    from unipre3d_b200 import fused_encoder
+    from unipre3d_b200.backbone import TransformerEncoder
+    enc = TransformerEncoder(embed_dim=384, depth=3, num_heads=6, drop_path_rate=[0.0, 0.05, 0.1])
+    ps = fused_encoder.stack_parameters(enc.blocks)
+    assert len(ps) == 3 * fused_encoder.PARAMS_PER_BLOCK == len(list(enc.parameters()))
+    assert {id(p) for p in ps} == {id(p) for p in enc.parameters()}
+    assert fused_encoder.supports(enc.blocks)
+    assert not fused_encoder.supports(TransformerEncoder(embed_dim=48, depth=1, num_heads=6).blocks)       # width % 128
+    assert not fused_encoder.supports(TransformerEncoder(embed_dim=128, depth=1, num_heads=2, qkv_bias=True).blocks)
+    assert not fused_encoder.supports(TransformerEncoder(embed_dim=128, depth=1, num_heads=2, drop_rate=0.1).blocks)
+
+
+def test_lazy_visibility_filter_is_evaluated_on_demand():
+    import torch
+    from unipre3d_b200.gaussian_renderer import _LazyVisibility
+    radii = [torch.tensor([[0, 3, 0], [1, 0, 2]]), torch.tensor([[5, 0, 0], [0, 0, 0]])]
+    vis = _LazyVisibility(radii)
+    assert vis._vis is None and len(vis) == 2
+    assert torch.equal(vis[1], radii[1] > 0) and vis._vis is not None
+    assert [v.dtype for v in vis] == [torch.bool, torch.bool]
