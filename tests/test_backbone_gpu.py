@@ -417,3 +417,23 @@ def test_fused_feature_fusion_matches_module_path():
     assert torch.allclose(outs[False][0], outs[True][0], atol=2e-5, rtol=1e-4)
     for a, b in zip(outs[False][1], outs[True][1]):
         assert torch.allclose(a, b, atol=1e-4 * float(b.abs().max()) + 1e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("act", [torch.float32, torch.bfloat16])
+def test_fused_layer_norm_matches_module(act):
+    from unipre3d_b200.fused_encoder import fused_layer_norm
+    torch.manual_seed(11)
+    norm = torch.nn.LayerNorm(384).to(DEV)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5); norm.bias.normal_()
+    x = torch.randn(4, 129, 384, device=DEV, requires_grad=True)
+    w = torch.randn(4, 129, 384, device=DEV)
+    ref = norm(x)
+    g_ref = torch.autograd.grad((ref * w).sum(), [x, norm.weight, norm.bias])
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=act == torch.bfloat16):
+        out = fused_layer_norm(norm, x)
+    assert out.dtype == act and torch.allclose(out.float(), ref, **_tol(act))
+    g = torch.autograd.grad((out.float() * w).sum(), [x, norm.weight, norm.bias])
+    tol = 1e-4 if act == torch.float32 else 2e-2
+    for a, b in zip(g, g_ref):
+        assert float((a - b).abs().max()) <= tol * float(b.abs().max()) + 1e-5

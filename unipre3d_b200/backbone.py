@@ -221,5 +221,9 @@ class PointTransformerEncoder(nn.Module):
         x = torch.cat((cls_tokens, group_input_tokens), dim=1)
         pos = torch.cat((cls_pos, pos), dim=1)
         x = self.blocks.forward(x, pos, center, image_features, c2w_projection_matrix, intricsic, feature_fusion)
-        x = self.norm(x)
+        if x.is_cuda and not getattr(self.blocks, "force_module_path", False):
+            from .fused_encoder import fused_layer_norm
+            x = fused_layer_norm(self.norm, x)
+        else:
+            x = self.norm(x)
         return x[:, 1:, :], center

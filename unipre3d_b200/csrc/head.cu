@@ -127,7 +127,7 @@ splat_head_bwd_kernel(int P, int M, int Cr, const float *__restrict__ raw, const
 constexpr int FUS_MAX_N = 1024;     // group centres per object held in shared memory
 constexpr int FUS_MAX_G = 64;
 
-// One CTA per object b.  center (B,N,3); w2c (B,16) row-major world-to-camera (the inverse the host computed);
+// grid (objects, slices): blockIdx.x = object b.  center (B,N,3); w2c (B,16) row-major world-to-camera (the inverse the host computed);
 // image (B,3,H,W) is the source view of object b; the analytic stem field f[c] = sin(proj[c,:].rgb + shift[c]) is
 // normalised with image_conv's GroupNorm statistics (sums (B,G,2) fp64 = [sum f, sum f^2] per group).
 // Outputs: keep (B,N) uint8, pix (B,N,2) int32 (ix, iy; 0 where the point is outside), xhat (B,N,Cc) fp32 =
@@ -159,8 +159,10 @@ fusion_project_kernel(int N, int H, int W, int Cc, int G, float fx, float fy, fl
         const int ix = inside ? (int)px : 0, iy = inside ? (int)py : 0;
         s_cell[p] = inside ? iy * H + ix : -1;
         s_depth[p] = cam[2];
-        pix[((size_t)b * N + p) * 2] = ix;
-        pix[((size_t)b * N + p) * 2 + 1] = iy;
+        if (blockIdx.y == 0) {
+            pix[((size_t)b * N + p) * 2] = ix;
+            pix[((size_t)b * N + p) * 2 + 1] = iy;
+        }
         const float *img = image + (size_t)b * 3 * H * W + (size_t)ix * W + iy;             // image[b, :, ix, iy]
         s_rgb[p][0] = img[0]; s_rgb[p][1] = img[(size_t)H * W]; s_rgb[p][2] = img[(size_t)2 * H * W];
     }
@@ -183,9 +185,11 @@ fusion_project_kernel(int N, int H, int W, int Cc, int G, float fx, float fy, fl
                 if (s_cell[q] == c) dmin = fminf(dmin, s_depth[q]);
             k = s_depth[p] == dmin;                             // nearest point of the pixel (ties keep all, as the reference)
         }
-        keep[(size_t)b * N + p] = k ? 1 : 0;
+        if (blockIdx.y == 0) keep[(size_t)b * N + p] = k ? 1 : 0;
     }
-    for (int i = threadIdx.x; i < N * Cc; i += HEAD_THREADS) {
+    // the N x C field evaluation (one sinf per element) is spread over gridDim.y CTAs per object; each of them redoes the
+    // cheap projection above (with one CTA per object this loop alone was 20 of the kernel's 25 us)
+    for (int i = blockIdx.y * HEAD_THREADS + threadIdx.x; i < N * Cc; i += HEAD_THREADS * gridDim.y) {
         const int p = i / Cc, c = i - p * Cc, g = c / cpg;
         float a = __fmul_rn(s_rgb[p][0], proj[3 * c]);
         a = __fmaf_rn(s_rgb[p][1], proj[3 * c + 1], a);
@@ -232,8 +236,9 @@ extern "C" int up3d_fusion_project(int B, int N, int H, int W, int C, int G, flo
     UP3D_CHECK_ARG(C > 0 && G > 0 && G <= FUS_MAX_G && C % G == 0, "up3d_fusion_project: need C %% G == 0, G <= %d", FUS_MAX_G);
     if (B == 0) return 0;
     UP3D_CHECK_ARG(center && w2c && image && proj && shift && sums && keep && pix && xhat, "up3d_fusion_project: NULL pointer");
-    fusion_project_kernel<<<B, HEAD_THREADS, 0, (cudaStream_t)stream>>>(N, H, W, C, G, fx, fy, cx, cy, eps, center, w2c, image, proj,
-                                                                         shift, sums, keep, pix, xhat);
+    const int slices = max(1, min(16, div_up(N * C, HEAD_THREADS * 8)));
+    fusion_project_kernel<<<dim3(B, slices), HEAD_THREADS, 0, (cudaStream_t)stream>>>(N, H, W, C, G, fx, fy, cx, cy, eps, center, w2c,
+                                                                                       image, proj, shift, sums, keep, pix, xhat);
     UP3D_LAUNCH_OK("fusion_project_kernel");
     return 0;
 }

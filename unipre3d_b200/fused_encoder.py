@@ -280,6 +280,47 @@ class EncoderStackFn(torch.autograd.Function):
         return (gx, gp, None, None) + tuple(grads)
 
 
+class FusedLayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dimension through up3d_ln_fwd / up3d_ln_bwd (1 launch each way instead of 2 + 3); used
+    for the encoder's final `self.norm` (transformer.py:325)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, act_dtype):
+        require_cuda(x)
+        shape = x.shape
+        C = shape[-1]
+        x2 = x.reshape(-1, C).contiguous().float()
+        with torch.cuda.device(x.device):
+            _, y, mean, rstd = ln_fwd(x2, None, None, None, weight, bias, eps, x2.shape[0], act_dtype, want_xs=False)
+        ctx.save_for_backward(x2, mean, rstd, weight)
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, weight = ctx.saved_tensors
+        C = x2.shape[1]
+        dy2 = dy.reshape(-1, C).contiguous()
+        if dy2.dtype not in (torch.float32, torch.bfloat16):
+            dy2 = dy2.float()
+        dwb = torch.zeros(2 * C, dtype=torch.float32, device=x2.device)
+        with torch.cuda.device(x2.device):
+            dx, _ = ln_bwd(dy2, x2, mean, rstd, weight, None, None, x2.shape[0], None, False, dwb[:C], dwb[C:], None)
+        return dx.view(ctx.shape), dwb[:C], dwb[C:], None, None
+
+
+def fused_layer_norm(norm, x):
+    """norm: nn.LayerNorm; x (..., C) on CUDA -> LayerNorm(x) in the autocast dtype (fp32 without autocast)."""
+    act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+    C = x.shape[-1]
+    ok = (x.is_cuda and isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+          and tuple(norm.normalized_shape) == (C,) and C % 128 == 0 and C // 128 in (1, 2, 3, 4, 6, 8)
+          and act in (torch.float32, torch.bfloat16))
+    if not ok:
+        return norm(x)
+    return FusedLayerNormFn.apply(x, norm.weight, norm.bias, float(norm.eps), act)
+
+
 def supports(blocks) -> bool:
     """The fused stack covers the configuration the reference instantiates (qkv_bias=False, no dropout, erf-GELU,
     LayerNorm with affine parameters, width a multiple of 128)."""
