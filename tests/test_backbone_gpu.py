@@ -414,6 +414,23 @@ def test_fused_feature_fusion_matches_module_path():
         outs[force] = (y.detach(), g)
     keep, mapped, pix = fusion.fused_project_and_sample(fusion.LazyImageFeatures(field, conv), center, c2w[:, 0], K)
     assert 0 < int(keep.sum()) < B * N and not bool(keep[:, 7].any())
+    # index work against the eager restatement: pixel coordinates, in-image test and nearest-depth test.  (A projected
+    # coordinate that lands within an ulp of x.5 may round differently between cuBLAS' and the kernel's summation order:
+    # allow a vanishing fraction of such points, none is expected on this seed.)
+    with torch.no_grad():
+        pi_xy, depth = fusion.FeatureFusion.project_points_to_image(center, c2w[:, 0], K)
+        fx_, fy_ = pi_xy[..., 0], pi_xy[..., 1]
+        inside = (fx_ >= 0) & (fy_ >= 0) & (fx_ < R) & (fy_ < R) & (depth >= 0)
+        ix = torch.where(inside, fx_, torch.zeros_like(fx_)).int()
+        iy = torch.where(inside, fy_, torch.zeros_like(fy_)).int()
+        cell = torch.arange(B, device=DEV).unsqueeze(1) * (R * R) + iy.long() * R + ix.long()
+        dm = torch.where(inside, depth, torch.full_like(depth, float("inf")))
+        zbuf = torch.full((B * R * R + R * R,), float("inf"), device=DEV)
+        zbuf.scatter_reduce_(0, cell.reshape(-1), dm.reshape(-1), reduce="amin", include_self=True)
+        keep_ref = inside & (depth == zbuf[cell])
+    same_pix = (pix[..., 0] == ix) & (pix[..., 1] == iy)
+    assert float(same_pix.float().mean()) >= 0.995 and float((keep == keep_ref).float().mean()) >= 0.995
+    assert bool(keep[same_pix].eq(keep_ref[same_pix]).all()) or float((keep == keep_ref).float().mean()) >= 0.998
     assert torch.allclose(outs[False][0], outs[True][0], atol=2e-5, rtol=1e-4)
     for a, b in zip(outs[False][1], outs[True][1]):
         assert torch.allclose(a, b, atol=1e-4 * float(b.abs().max()) + 1e-6, rtol=1e-4)
