@@ -454,3 +454,76 @@ def test_fused_layer_norm_matches_module(act):
     tol = 1e-4 if act == torch.float32 else 2e-2
     for a, b in zip(g, g_ref):
         assert float((a - b).abs().max()) <= tol * float(b.abs().max()) + 1e-5
+
+
+@pytest.mark.parametrize("name,deg,iso", [("deg1", 1, False), ("deg0_iso", 0, True)])
+def test_splat_head_kernel_matches_reference_golden_and_oracle(name, deg, iso):
+    """csrc/head.cu splat head against the golden vectors generated from the reference's own
+    `_process_network_output` (tests/golden/process_output.npz) and against the numpy oracle."""
+    from oracle import backbone_oracle as bo
+    from unipre3d_b200.gaussian_predictor import SplatHeadFn
+    z = np.load(os.path.join(G, "process_output.npz"))
+    raw, center = z[f"{name}.raw"], z[f"{name}.center"]
+    M = (deg + 1) ** 2
+    xyz, op, sc, rot, shs = SplatHeadFn.apply(torch.tensor(raw, device=DEV).permute(0, 2, 1), torch.tensor(center, device=DEV),
+                                              M, 0.7, iso)
+    got = {"xyz": xyz, "opacity": op, "scaling": sc, "rotation": rot, "features_dc": shs[:, :, :1]}
+    if deg > 0:
+        got["features_rest"] = shs[:, :, 1:]
+    ref = bo.splat_head(raw, center, 0.7, iso, deg)
+    for k, v in got.items():
+        gold = z[f"{name}.out.{k}"]
+        assert tuple(v.shape) == gold.shape, k
+        np.testing.assert_allclose(v.cpu().numpy(), gold, atol=2e-6, rtol=1e-5, err_msg=k)
+        np.testing.assert_allclose(v.cpu().numpy(), ref[k], atol=2e-6, rtol=1e-5, err_msg=k)
+
+
+def test_fusion_project_kernel_matches_oracle_geometry():
+    import math
+    from oracle import backbone_oracle as bo
+    from unipre3d_b200 import camera as cam
+    from unipre3d_b200 import fusion
+    from unipre3d_b200.gaussian_predictor import StemFeatureField
+    torch.manual_seed(12)
+    B, N, R, Cin, G_ = 3, 128, 48, 128, 32
+    fov = 49.13434264120263
+    proj_m = cam.get_projection_matrix(0.5, 2.0, math.radians(fov), math.radians(fov))
+    c2w = torch.stack([cam.make_view(*cam.look_at_pose(70.0 * i, 25.0, 1.75), proj_m)["view_to_world_transform"]
+                       for i in range(B)])
+    K = np.zeros((3, 4)); focal = (R / 2.0) / math.tan(math.radians(fov / 2.0))
+    K[0, 0] = K[1, 1] = focal; K[0, 2] = K[1, 2] = R / 2.0; K[2, 2] = 1
+    center = torch.randn(B, N, 3) * 0.35
+    center[:, 9] = center[:, 8] * 1.03
+    field = StemFeatureField(torch.rand(B, 3, R, R, device=DEV), torch.randn(Cin, 3, device=DEV) * 0.7,
+                             torch.randn(Cin, device=DEV) * 0.3)
+    conv = torch.nn.Sequential(torch.nn.GroupNorm(G_, Cin, eps=1e-6), torch.nn.Conv2d(Cin, 16, 1)).to(DEV)
+    keep, _, pix = fusion.fused_project_and_sample(fusion.LazyImageFeatures(field, conv), center.to(DEV), c2w.to(DEV), K)
+    ix, iy, inside, keep_ref, _ = bo.fusion_geometry(center.numpy(), c2w.numpy(), K, R, R)
+    pix = pix.cpu().numpy()
+    same = (pix[..., 0] == ix) & (pix[..., 1] == iy)
+    assert same.mean() >= 0.995 and (keep.cpu().numpy() == keep_ref).mean() >= 0.995
+    assert 0 < keep_ref.sum() < B * N
+
+
+def test_fused_clip_adamw_matches_numpy_oracle():
+    from oracle import backbone_oracle as bo
+    from unipre3d_b200.optim import FusedClipAdamW
+    shapes = [(96, 40), (513,), (5, 3, 2)]
+    ps = _clone_params(shapes, 3)
+    opt = FusedClipAdamW([{"params": ps[:2], "lr": 2e-3}, {"params": ps[2:], "lr": 1e-3}], lr=0.0, eps=1e-15, max_norm=1.0)
+    opt.grad_scale = 0.5
+    P = [p.detach().cpu().double().numpy().copy() for p in ps]
+    M = [np.zeros_like(p) for p in P]; V = [np.zeros_like(p) for p in P]
+    step = 0
+    for it in range(3):
+        gg = torch.Generator(device="cpu").manual_seed(50 + it)
+        grads = [torch.randn(s, generator=gg) * (0.05 if it == 0 else 20.0) for s in shapes]
+        for p, g in zip(ps, grads):
+            p.grad = g.to(DEV)
+        opt.step()
+        step, total, applied = bo.clip_adamw_step(P, [g.double().numpy() for g in grads], M, V, step, [2e-3, 2e-3, 1e-3],
+                                                  grad_scale=0.5)
+        assert applied and abs(opt.last_total_norm() - total) <= 1e-5 * total
+        for p, q in zip(ps, P):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), q, atol=2e-6, rtol=2e-5)
+    assert opt.step_count() == step == 3
