@@ -185,3 +185,61 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_sd_vae_image_branch_architecture():
+    """image_predictor.AutoencoderKL restates the sd-vae-ft-mse architecture the reference loads through diffusers
+    (model/image_predictor.py:26-31): parameter count of the public checkpoint, diffusers' state-dict names, the four
+    hooked decoder blocks with `decoder_block_3` = 128 channels at image resolution; frozen and deterministic."""
+    import torch
+    from unipre3d_b200.image_predictor import AutoencoderKL, ImageFeaturePredictor, count_parameters
+    torch.manual_seed(0)
+    ip = ImageFeaturePredictor(None, [128])
+    assert count_parameters(ip.encoder) == 83_653_863
+    sd = ip.encoder.state_dict()
+    assert len(sd) == 248
+    for k in ("encoder.down_blocks.1.resnets.0.conv_shortcut.weight", "encoder.down_blocks.2.downsamplers.0.conv.weight",
+              "encoder.mid_block.attentions.0.to_q.weight", "encoder.mid_block.attentions.0.group_norm.bias",
+              "decoder.up_blocks.2.upsamplers.0.conv.bias", "decoder.up_blocks.3.resnets.2.conv2.weight",
+              "decoder.mid_block.attentions.0.to_out.0.weight", "quant_conv.weight", "post_quant_conv.bias"):
+        assert k in sd, k
+    assert "encoder.down_blocks.3.downsamplers.0.conv.weight" not in sd and "decoder.up_blocks.3.upsamplers.0.conv.weight" not in sd
+    assert not any(p.requires_grad for p in ip.parameters())
+    ip.train()
+    assert not ip.encoder.training                                # the reference keeps the VAE in eval mode
+    x = torch.rand(1, 3, 32, 32)
+    a, b = ip(x), ip(x)
+    assert {k: tuple(v.shape) for k, v in a.items()} == {"decoder_block_0": (1, 512, 8, 8), "decoder_block_1": (1, 512, 16, 16),
+                                                         "decoder_block_2": (1, 256, 32, 32), "decoder_block_3": (1, 128, 32, 32)}
+    assert all(torch.equal(a[k], b[k]) for k in a) and all(torch.isfinite(v).all() for v in a.values())
+    # stopping after the last hooked block gives the same features as decoding to RGB
+    feats = {}
+    rgb = ip.encoder(x, collect=feats)
+    assert rgb.shape == (1, 3, 32, 32) and torch.equal(feats["decoder_block_3"], a["decoder_block_3"])
+    # a checkpoint in diffusers' layout loads strictly
+    m2 = AutoencoderKL()
+    m2.load_state_dict(sd, strict=True)
+
+
+def test_predictor_selects_image_branch():
+    import torch
+    from unipre3d_b200.config import compose
+    from unipre3d_b200.fusion import LazyImageFeatures
+    from unipre3d_b200.gaussian_predictor import FrozenImageStem, GaussianSplatPredictor
+    from unipre3d_b200.image_predictor import ImageFeaturePredictor
+    assert isinstance(GaussianSplatPredictor(compose()).image_network, FrozenImageStem)
+    m = GaussianSplatPredictor(compose(overrides=["model.image_branch=sdvae", "data.training_resolution=32"]))
+    assert isinstance(m.image_network, ImageFeaturePredictor)
+    trainable = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert trainable and not any(n.startswith("image_network.") for n in trainable)
+    # the VAE's dense features feed the sampled image_conv evaluation
+    feats = m.image_network(torch.rand(2, 3, 32, 32))["decoder_block_3"]
+    lazy = LazyImageFeatures(feats, m.image_conv)
+    bidx = torch.arange(2).unsqueeze(1).expand(2, 5)
+    ix, iy = torch.randint(0, 32, (2, 5)), torch.randint(0, 32, (2, 5))
+    assert torch.allclose(lazy.sample(bidx, ix, iy), lazy.dense()[bidx, :, ix, iy], atol=1e-4, rtol=1e-4)
+    try:
+        GaussianSplatPredictor(compose(overrides=["model.image_branch=nope"]))
+        assert False
+    except ValueError:
+        pass

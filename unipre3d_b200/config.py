@@ -58,7 +58,7 @@ _SETTINGS = {
     "opt": {"betas": [0.9, 0.999], "imgs_per_obj": 4,
             "ema": {"use": True, "update_every": 10, "update_after_step": 100, "beta": 0.9999},
             "lambda_lpips": 0.01, "pretrained_ckpt": None, "record_img": True},
-    "model": {"max_sh_degree": 1, "isotropic": False},
+    "model": {"max_sh_degree": 1, "isotropic": False, "image_branch": "stem", "vae_weights": None},
     "logging": {"ckpt_iterations": 2000, "val_log": 2000, "loss_log": 10, "loop_log": 2000, "render_log": 2000,
                 "centered": True},
 }

@@ -194,7 +194,17 @@ class GaussianSplatPredictor(nn.Module):
             raise NotImplementedError("opt.level='scene' (SURVEY.md §8a rows P1/P2) needs the sparse-conv backbones")
         pretrained = getattr(cfg.opt, "pretrained_ckpt", None)
         if self.use_fusion:
-            self.image_network = FrozenImageStem(cfg, [128])
+            # image branch: "stem" (default) = weight-free analytic stand-in; "sdvae" = the reference's frozen
+            # Stable-Diffusion VAE architecture (image_predictor.py; random-init unless model.vae_weights names the
+            # reference's weights/diffusion_pytorch_model.bin)
+            self.image_branch = str(getattr(cfg.model, "image_branch", "stem")).lower()
+            if self.image_branch == "sdvae":
+                from .image_predictor import ImageFeaturePredictor
+                self.image_network = ImageFeaturePredictor(cfg, [128], pretrained_path=getattr(cfg.model, "vae_weights", None))
+            elif self.image_branch == "stem":
+                self.image_network = FrozenImageStem(cfg, [128])
+            else:
+                raise ValueError(f"model.image_branch={self.image_branch!r} (expected 'stem' or 'sdvae')")
             self.point_network = PointFeaturePredictor(cfg, self.split_dimensions, pretrained_path=pretrained)
             mc = self.MODEL_CONFIGS[cfg.model.backbone_type]
             in_dim = self.image_network.encoder_config["block_out_channels"][0]
@@ -249,6 +259,9 @@ class GaussianSplatPredictor(nn.Module):
         if getattr(self.cfg.model, "dense_image_features", False):
             image_output = self.image_network.forward(image)
             image_features = self.image_conv.forward(image_output["decoder_block_3"])     # reference dataflow
+        elif self.image_branch == "sdvae":
+            # dense (n,128,R,R) decoder features from the frozen VAE; image_conv is still evaluated only at the sampled pixels
+            image_features = LazyImageFeatures(self.image_network.forward(image)["decoder_block_3"], self.image_conv)
         else:
             image_output = self.image_network.forward(image, lazy=True)
             image_features = LazyImageFeatures(image_output["decoder_block_3"], self.image_conv)
