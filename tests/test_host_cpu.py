@@ -243,3 +243,24 @@ def test_predictor_selects_image_branch():
         assert False
     except ValueError:
         pass
+
+
+def test_checkpoint_round_trip_keeps_reference_keys(tmp_path):
+    """ModelManager.save_checkpoint / load_checkpoint: the reference's checkpoint dict (train_network.py:200-210)."""
+    import torch
+    from unipre3d_b200.config import compose
+    from unipre3d_b200.trainer import ModelManager
+    cfg = compose(overrides=["data.training_resolution=32", "opt.batch_size=2"])
+    torch.manual_seed(0)
+    a = ModelManager(cfg, torch.device("cpu"))
+    a.save_latest_checkpoint(123, 21.5, str(tmp_path))
+    ck = torch.load(tmp_path / "model_latest.pth")
+    assert set(ck) == {"iteration", "optimizer_state_dict", "model_state_dict", "best_PSNR"}
+    assert any(k.startswith("point_network.encoder.blocks.blocks.0.attn.qkv") for k in ck["model_state_dict"])
+    torch.manual_seed(1)
+    b = ModelManager(cfg, torch.device("cpu"))
+    assert not torch.equal(b.model.fusion_mlps[0].weight, a.model.fusion_mlps[0].weight)
+    meta = b.load_checkpoint(str(tmp_path / "model_latest.pth"))
+    assert meta == {"iteration": 123, "best_PSNR": 21.5}
+    for (ka, pa), (kb, pb) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
+        assert ka == kb and torch.equal(pa, pb), ka

@@ -156,6 +156,34 @@ class ModelManager:
                     "model_state_dict": (self.ema.ema_model.state_dict() if self.ema else self.model.state_dict()),
                     "best_PSNR": best_psnr}, save_path)
 
+    def save_latest_checkpoint(self, iteration: int, best_psnr: float, save_dir: str) -> None:
+        """train_network.py:212-215."""
+        self.save_checkpoint(iteration, best_psnr, os.path.join(save_dir, "model_latest.pth"))
+
+    def save_best_checkpoint(self, iteration: int, best_psnr: float, save_dir: str) -> None:
+        """train_network.py:217-220."""
+        self.save_checkpoint(iteration, best_psnr, os.path.join(save_dir, "model_best.pth"))
+
+    def load_checkpoint(self, path: str, load_optimizer: bool = True) -> Dict[str, float]:
+        """Resume from a checkpoint written by `save_checkpoint` (or by the reference's ModelManager: same keys).
+        Frozen image-network weights absent from the file keep their current values."""
+        ckpt = torch.load(path, map_location=self.device)
+        info = self.model.load_state_dict(ckpt["model_state_dict"], strict=False)
+        bad = [k for k in info.missing_keys if not k.startswith("image_network.")] + list(info.unexpected_keys)
+        if bad:
+            raise RuntimeError(f"checkpoint does not match the model: {bad[:8]}")
+        if self.ema:
+            self.ema.ema_model.load_state_dict(ckpt["model_state_dict"], strict=False)
+        if load_optimizer and "optimizer_state_dict" in ckpt:
+            self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        for m in self.model.modules():          # bf16 weight shadows (mixed_precision.ShadowWeights) follow the masters
+            w16 = getattr(m, "_w16", None)
+            if w16 is not None:
+                w16.copy_(m.weight.detach().reshape(w16.shape))
+                if getattr(m, "_b16", None) is not None:
+                    m._b16.copy_(m.bias.detach())
+        return {"iteration": int(ckpt.get("iteration", 0)), "best_PSNR": float(ckpt.get("best_PSNR", 0.0))}
+
 
 class ValidationManager:
     def __init__(self, cfg, device):
