@@ -362,6 +362,15 @@ UP3D_API int up3d_fusion_project(int B, int N, int H, int W, int C, int G, float
                                  up3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Point-cloud serialization keys (first stage of PTv3: pointcept/models/utils/structure.py:47-107 `Point.serialization`,
+ * serialization/default.py:8-25 `encode`, serialization/z_order.py:41-96).  grid_coord (n,3) int32 voxel coordinates,
+ * batch (n) int64 or NULL -> code (n) int64: bit i of x, y, z at bits 3i+2, 3i+1, 3i (swap_xy != 0: the "z-trans" order,
+ * x and y exchanged), batch index OR-ed in above bit 3*depth; depth in [1,16] as the reference asserts.
+ * ---------------------------------------------------------------------------------------- */
+UP3D_API int up3d_zorder_keys(int64_t n, int depth, int swap_xy, const int32_t *grid_coord, const int64_t *batch, int64_t *code,
+                              up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Frozen image stem (stand-in for model/image_predictor.py:56-81, whose SD-VAE weights are not shipped):
  * the 128-channel field f[n,c,y,x] = sin(proj[c,:] . image[n,:,y,x] + shift[c]) feeds
  * image_conv = GroupNorm(G, C) + Conv1x1 (model/gaussian_predictor.py:61-66,139).  Writes the GroupNorm

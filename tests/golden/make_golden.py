@@ -275,10 +275,36 @@ def blocks_only():
     print("wrote transformer_blocks_w128.npz")
 
 
+def serialization_fixture():
+    """serialization.npz : pointcept/models/utils/serialization (encode: z / z-trans, with batch) on voxel coordinates --
+    the reference's own functions, loaded straight from /root/reference."""
+    pkg = stub("ref_serialization"); pkg.__path__ = [os.path.join(REF, "pointcept/models/utils/serialization")]
+    z = load("ref_serialization.z_order", os.path.join(REF, "pointcept/models/utils/serialization/z_order.py"))
+    h = load("ref_serialization.hilbert", os.path.join(REF, "pointcept/models/utils/serialization/hilbert.py"))
+    d = load("ref_serialization.default", os.path.join(REF, "pointcept/models/utils/serialization/default.py"))
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for name, n, depth, nb in (("small", 257, 7, 3), ("deep", 1000, 16, 5), ("bigbatch", 64, 10, 300)):
+        hi = (1 << depth)
+        coord = torch.randint(0, hi, (n, 3), generator=g, dtype=torch.int32)
+        coord[0] = hi - 1                                      # all bits set
+        coord[1] = 0
+        batch = torch.sort(torch.randint(0, nb, (n,), generator=g))[0]
+        out[f"{name}.coord"], out[f"{name}.batch"], out[f"{name}.depth"] = coord.numpy(), batch.numpy(), np.int64(depth)
+        for o in ("z", "z-trans"):
+            out[f"{name}.code.{o}"] = d.encode(coord, batch, depth, order=o).numpy()
+        out[f"{name}.code_nobatch.z"] = d.encode(coord, None, depth, order="z").numpy()
+    np.savez_compressed(os.path.join(OUT, "serialization.npz"), **out)
+    print("wrote serialization.npz")
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
-    if len(sys.argv) > 1 and sys.argv[1] == "blocks":
+    if len(sys.argv) > 1 and sys.argv[1] == "serialization":
+        serialization_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "blocks":
         blocks_only()
     else:
         main()
         blocks_only()
+        serialization_fixture()
