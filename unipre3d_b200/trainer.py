@@ -234,6 +234,9 @@ class Trainer:
         self._grad_sync = None
         if self.world > 1:
             self._setup_grad_sync()
+        else:
+            from . import fused_encoder
+            fused_encoder.GRAD_READY_HOOK = None      # a hook left by an earlier data-parallel Trainer of this process
         self.iteration = 0
         self._graph = None
         self._static: Optional[dict] = None
