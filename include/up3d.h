@@ -380,6 +380,28 @@ UP3D_API int up3d_zorder_keys(int64_t n, int depth, int swap_xy, const int32_t *
 UP3D_API int up3d_stem_group_stats(int n_images, int H, int W, int C, int G, const float *image, const float *proj,
                                    const float *shift, double *sums, up3d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense Linear on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulator, TMA tensor loads).
+ * Replaces the nn.Linear / Conv1d(k=1) GEMMs of the point backbone
+ * (/root/reference/openpoints/models/backbone/transformer.py:22-33 Mlp, :52-77 Attention qkv/proj,
+ * :214-243 mini-PointNet), forward and the dX half of the backward.
+ *   out (T,N) = A (T,K) bf16 row-major  x  op(B)  (+ bias (N) bf16)  -> epilogue
+ *   b_major 0: B is (N,K) row-major (the weight as nn.Linear stores it: y = x W^T)
+ *   b_major 1: B is (K,N) row-major (the same weight read for dx = dy W)
+ *   b_major | 2: B is an activation written by a kernel that may still be in flight (by default B is treated as a
+ *              weight and prefetched before the programmatic dependency on the previous kernel resolves)
+ *   epilogue 0: out = acc (+ bias)
+ *            1: aux_out (T,N) bf16 = acc + bias ; out = GELU(aux_out)          (fc1 + nn.GELU)
+ *            2: out = acc * GELU'(aux_in (T,N) bf16)                          (dX of fc2 + GELU backward)
+ *   out is bf16 (out_f32 = 0) or fp32 (out_f32 = 1); tile_n = 0 lets the library choose the CTA tile width
+ *   (32/64/96/128; 64/128 for b_major 1) and the split-K factor; otherwise tile_n = width | (split_k << 16), split_k in
+ *   {0 = auto, 1, 2, 4} (2 and 4: the K range is shared by a thread-block cluster; plain epilogue only).  K % 8 == 0, N % 32 == 0, all pointers 16-byte aligned.
+ * ---------------------------------------------------------------------------------------- */
+/* Programmatic dependent launch of the library's chained kernels (default on; UP3D_PDL=0 in the environment = off). */
+UP3D_API int up3d_set_pdl(int enabled);
+UP3D_API int up3d_tc_linear(int T, int N, int K, const void *A, const void *B, int b_major, const void *bias, int epilogue,
+                            const void *aux_in, void *aux_out, void *out, int out_f32, int tile_n, up3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@ Third-party modules the reference imports but that are absent here (timm, spconv
 replaced by minimal stubs; the CUDA-only tokenizer (SubsampleGroup) is stubbed by precomputed groups so the fixtures
 pin the ARITHMETIC of the reference modules:
   transformer_encoder.npz : openpoints/models/backbone/transformer.py  PointTransformerEncoder (small config) fwd + grads
+  transformer_encoder_w128.npz : the same module at width 128 / head_dim 64 (the widths the CUDA fused paths accept)
   feature_fusion.npz      : fusion/feat_fusion.py  FeatureFusion.__call__
   process_output.npz      : model/gaussian_predictor.py  _process_network_output / _init_activations (object level)
   utils.npz               : utils/loss_utils.py focal_l2_loss, utils/graphics_utils.py matrices, utils/sh_utils.py eval_sh
@@ -275,6 +276,60 @@ def blocks_only():
     print("wrote transformer_blocks_w128.npz")
 
 
+def encoder_w128():
+    """transformer_encoder_w128.npz : the WHOLE PointTransformerEncoder (transformer.py:246-327) at a width the CUDA fused
+    paths accept (trans_dim 128 = one LayerNorm vector group, head_dim 64 = the own attention kernel, 32 x 16-point
+    groups through the fused mini-PointNet), train-mode forward + all gradients -- pins the composition of mini-PointNet,
+    reduce_dim, cls/pos embedding, fused Block stack, FeatureFusion and the final norm on the GPU."""
+    stub("timm"); stub("timm.models")
+    stub("timm.models.layers", DropPath=_DropPath, trunc_normal_=torch.nn.init.trunc_normal_)
+    stub("openpoints"); stub("openpoints.models")
+    stub("openpoints.models.build", MODELS=_Registry())
+    stub("openpoints.models.layers", SubsampleGroup=_FixedGroups)
+    ff = load("ref_feat_fusion", os.path.join(REF, "fusion/feat_fusion.py"))
+    stub("fusion", FeatureFusion=ff.FeatureFusion)
+    tr = load("ref_transformer", os.path.join(REF, "openpoints/models/backbone/transformer.py"))
+    torch.manual_seed(7)
+    B, G, K, R, ed, td, depth, heads = 2, 32, 16, 24, 128, 128, 2, 2
+    enc = tr.PointTransformerEncoder(in_channels=3, num_groups=G, group_size=K, encoder_dims=ed, trans_dim=td, depth=depth,
+                                     num_heads=heads, drop_path_rate=0.1)
+    with torch.no_grad():
+        for m in enc.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+        enc.cls_token.normal_(0, 0.02)
+    fusion_mlps = torch.nn.Sequential(torch.nn.Linear(2 * td, td), torch.nn.ReLU())
+    neigh = torch.randn(B, 3, G, K) * 0.05
+    center = torch.randn(B, G, 3) * 0.2
+    _FixedGroups.neighborhood, _FixedGroups.center = neigh, center
+    pts = torch.randn(B, 64, 3)
+    img_feat = torch.randn(B, td, R, R, requires_grad=True)
+    from unipre3d_b200 import camera as cam
+    import math
+    fov = 49.13434264120263
+    proj = cam.get_projection_matrix(0.5, 2.0, math.radians(fov), math.radians(fov))
+    c2w = torch.stack([cam.make_view(*cam.look_at_pose(30.0 * i, 20.0, 1.75), proj)["view_to_world_transform"] for i in range(B)]).unsqueeze(1)
+    K_in = np.zeros((3, 4)); focal = (R / 2.0) / math.tan(math.radians(fov / 2.0))
+    K_in[0, 0] = K_in[1, 1] = focal; K_in[0, 2] = K_in[1, 2] = R / 2.0; K_in[2, 2] = 1
+    enc.train()
+    for m in enc.modules():
+        if isinstance(m, _DropPath):
+            m.drop_prob = 0.0
+    out_tr, _ = enc(pts, img_feat, c2w, fusion_mlps, K_in)
+    wsum = torch.randn_like(out_tr)
+    (out_tr * wsum).sum().backward()
+    f16 = lambda a: a        # fp32 fixture: tolerances in the test are stated against exact reference values
+    np.savez_compressed(os.path.join(OUT, "transformer_encoder_w128.npz"),
+                        cfg=np.array([G, K, ed, td, depth, heads]), pts=pts.numpy(), neighborhood=neigh.numpy(),
+                        center=center.numpy(), img_feat=img_feat.detach().numpy(), c2w=c2w.numpy(), intrinsic=K_in,
+                        wsum=wsum.numpy(), out_train=out_tr.detach().numpy(), grad_img_feat=img_feat.grad.numpy(),
+                        fusion_w=fusion_mlps[0].weight.detach().numpy(), fusion_b=fusion_mlps[0].bias.detach().numpy(),
+                        grad_fusion_w=fusion_mlps[0].weight.grad.numpy(), grad_fusion_b=fusion_mlps[0].bias.grad.numpy(),
+                        **{"sd." + k: f16(v.detach().numpy()) for k, v in enc.state_dict().items()},
+                        **{"grad." + k: q.grad.numpy() for k, q in enc.named_parameters() if q.grad is not None})
+    print("wrote transformer_encoder_w128.npz")
+
+
 def serialization_fixture():
     """serialization.npz : pointcept/models/utils/serialization (encode: z / z-trans, with batch) on voxel coordinates --
     the reference's own functions, loaded straight from /root/reference."""
@@ -304,7 +359,10 @@ if __name__ == "__main__":
         serialization_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "blocks":
         blocks_only()
+    elif len(sys.argv) > 1 and sys.argv[1] == "encoder_w128":
+        encoder_w128()
     else:
         main()
         blocks_only()
+        encoder_w128()
         serialization_fixture()

@@ -527,3 +527,106 @@ def test_fused_clip_adamw_matches_numpy_oracle():
         for p, q in zip(ps, P):
             np.testing.assert_allclose(p.detach().cpu().numpy(), q, atol=2e-6, rtol=2e-5)
     assert opt.step_count() == step == 3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Whole-encoder parity on the GPU against the REFERENCE module's fixtures.
+#
+# bf16 tolerance model (stated, used by the three tests below): every GEMM operand/output of the bf16 path is rounded to
+# bf16 once (relative error <= 2^-9, rms ~2^-9/sqrt(3)); a Block has 8 such roundings on the residual path (y1, qkv, o, a,
+# y2, pre, h, d) and the residual stream itself stays fp32, so after `depth` blocks the error of an O(1)-normalised
+# activation is ~ 2^-9 * sqrt(8 * depth) rms; gradients see the same count again on the way back.  With a 4-sigma
+# allowance for the max over ~10^5 elements:  tol(depth) = 4 * 2^-9 * sqrt(8 * depth) for outputs, twice that for
+# gradients -- relative to the tensor's max-abs (plus the fixture's overall gradient scale for tiny tensors).
+def _bf16_tol(depth):
+    return 4.0 * 2.0 ** -9 * (8.0 * depth) ** 0.5
+
+
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_fused_stack_bf16_matches_reference_module_fixture(tc, monkeypatch):
+    """bf16 operands (the benchmarked precision; tcgen05 GEMMs when tc == "1", library GEMMs otherwise) against the
+    reference's own TransformerEncoder fixture, outputs and every parameter gradient."""
+    monkeypatch.setenv("UP3D_TC_LINEAR", tc)
+    from tests.test_golden_cpu import _blocks_from_fixture
+    z = np.load(os.path.join(G, "transformer_blocks_w128.npz"))
+    enc = _blocks_from_fixture(z).to(DEV)
+    depth = int(z["cfg"][3])
+    x = torch.tensor(z["x"], device=DEV, requires_grad=True)
+    pos = torch.tensor(z["pos"], device=DEV, requires_grad=True)
+    enc.train()
+    for m in enc.modules():
+        if m.__class__.__name__ == "DropPath":
+            m.drop_prob = 0.0
+    before = _lib_launches()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = enc(x, pos, None, None, None, None, None)
+    assert _lib_launches() > before
+    tol = _bf16_tol(depth)
+    err = np.abs(out.detach().float().cpu().numpy() - z["out"]).max()
+    assert err <= tol * np.abs(z["out"]).max(), (err, tol * np.abs(z["out"]).max())
+    (out.float() * torch.tensor(z["wsum"], device=DEV)).sum().backward()
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    checks = [("grad_x", x.grad), ("grad_pos", pos.grad)] + [("grad." + k, p.grad) for k, p in enc.named_parameters()]
+    for k, g in checks:
+        ref = z[k]
+        scale = np.abs(ref).max() + 1e-2 * gmax
+        e = np.abs(g.float().cpu().numpy() - ref).max()
+        assert e <= 2 * tol * scale, (k, e, 2 * tol * scale)
+
+
+@pytest.mark.parametrize("fixture", ["transformer_encoder.npz", "transformer_encoder_w128.npz"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_whole_encoder_on_gpu_matches_reference_fixture(mode, fixture):
+    """PointTransformerEncoder.forward (transformer.py:290-327: mini-PointNet -> reduce_dim -> cls/pos -> 16-block stack
+    -> FeatureFusion -> norm) on CUDA with the fixture's groups, against the reference module's outputs and gradients."""
+    from tests.test_golden_cpu import _encoder_from_fixture
+    z = np.load(os.path.join(G, fixture))
+    enc, fusion = _encoder_from_fixture(z)
+    enc, fusion = enc.to(DEV), fusion.to(DEV)
+    enc.group_divider.neigh = enc.group_divider.neigh.to(DEV)
+    enc.group_divider.center = enc.group_divider.center.to(DEV)
+    depth = int(z["cfg"][4])
+    pts, c2w = torch.tensor(z["pts"], device=DEV), torch.tensor(z["c2w"], device=DEV)
+    img = torch.tensor(z["img_feat"], device=DEV, requires_grad=True)
+    enc.train()
+    for m in enc.modules():
+        if m.__class__.__name__ == "DropPath":
+            m.drop_prob = 0.0
+    before = _lib_launches()
+    if mode == "bf16":
+        from unipre3d_b200.mixed_precision import ShadowWeights
+        shadow = ShadowWeights(torch.nn.ModuleList([enc, fusion]))     # noqa: F841  (the benchmarked configuration)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out, center = enc(pts, img, c2w, fusion, z["intrinsic"])
+        out = out.float()
+        # + the mini-PointNet's 4 GEMM roundings and the fusion / final-norm ones
+        tol_o = _bf16_tol(depth + 1)
+        tol_g = 2 * tol_o
+    else:
+        out, center = enc(pts, img, c2w, fusion, z["intrinsic"])
+        tol_o, tol_g = 1e-4, 2e-3
+    assert _lib_launches() > before, "the CUDA kernels did not run"
+    assert np.array_equal(center.cpu().numpy(), z["center"])
+    ref = z["out_train"]
+    err = np.abs(out.detach().cpu().numpy() - ref).max()
+    assert err <= tol_o * np.abs(ref).max() + 2e-5, (err, tol_o * np.abs(ref).max())
+    (out * torch.tensor(z["wsum"], device=DEV)).sum().backward()
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    e = np.abs(img.grad.cpu().numpy() - z["grad_img_feat"]).max()
+    assert e <= tol_g * (np.abs(z["grad_img_feat"]).max() + 1e-2 * gmax) + 1e-6, ("grad_img_feat", e)
+    n_checked = 0
+    for k, p in enc.named_parameters():
+        if "grad." + k not in z.files:
+            continue
+        ref = z["grad." + k]
+        if k in ("encoder.first_conv.0.bias", "encoder.second_conv.0.bias"):
+            continue        # zero-gradient biases in front of train-mode BatchNorm (see tests/test_golden_cpu.py)
+        scale = np.abs(ref).max() + (1e-2 if mode == "bf16" else 1e-4) * gmax
+        e = np.abs(p.grad.float().cpu().numpy() - ref).max()
+        assert e <= tol_g * scale + 2e-6, (k, e, tol_g * scale)
+        n_checked += 1
+    assert n_checked > 30
+    if "grad_fusion_w" in z.files:
+        for k, p in (("grad_fusion_w", fusion[0].weight), ("grad_fusion_b", fusion[0].bias)):
+            e = np.abs(p.grad.float().cpu().numpy() - z[k]).max()
+            assert e <= tol_g * (np.abs(z[k]).max() + 1e-2 * gmax) + 2e-6, (k, e)

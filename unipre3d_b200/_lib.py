@@ -82,6 +82,8 @@ def _load() -> C.CDLL:
         "up3d_adamw_step": (i32, [i32, i32] + [vp] * 10 + [f32] * 6 + [vp, vp]),
         "up3d_adamw_apply": (i32, [i32, i32] + [vp] * 10 + [f32] * 6 + [vp, vp]),
         "up3d_grad_sumsq": (i32, [i32, i32] + [vp] * 4 + [f32, vp, vp]),
+        "up3d_set_pdl": (i32, [i32]),
+        "up3d_tc_linear": (i32, [i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -103,7 +105,7 @@ EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_residen
             "up3d_bn_reduce_finalize", "up3d_gbn_stats", "up3d_gbn_apply_relu", "up3d_gbn_bwd_reduce", "up3d_gbn_bwd_apply",
             "up3d_group_max", "up3d_group_max_scatter", "up3d_group_combine", "up3d_attn_max_len", "up3d_attn_fwd",
             "up3d_attn_bwd", "up3d_splat_head_fwd", "up3d_splat_head_bwd", "up3d_fusion_project",
-            "up3d_zorder_keys"]
+            "up3d_zorder_keys", "up3d_tc_linear", "up3d_set_pdl"]
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0

@@ -105,6 +105,8 @@ __device__ __forceinline__ void am_store_acc(bf16 *dst, size_t row_stride, int r
 __global__ void __launch_bounds__(AM_FWD_THREADS)
 attn_fwd_mma_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, bf16 *__restrict__ o, float *__restrict__ lse) {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_trigger();
+    pdl_wait();
     const int Lp = am_round16(L), C = H * AM_D;
     bf16 *Ks = reinterpret_cast<bf16 *>(smem);
     bf16 *Vs = reinterpret_cast<bf16 *>(smem + am_align128((size_t)Lp * AM_LD * 2));
@@ -166,6 +168,8 @@ __global__ void __launch_bounds__(AM_BWD_THREADS)
 attn_bwd_mma_kernel(int L, int H, float scale, const bf16 *__restrict__ qkv, const bf16 *__restrict__ o,
                     const float *__restrict__ lse, const bf16 *__restrict__ dout, bf16 *__restrict__ dqkv) {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_trigger();
+    pdl_wait();
     const int Lp = am_round16(L), Lr = am_rows(L), C = H * AM_D;
     const size_t tile = am_align128((size_t)Lr * AM_LD * 2);
     bf16 *Qs = reinterpret_cast<bf16 *>(smem), *Ks = reinterpret_cast<bf16 *>(smem + tile);
@@ -284,8 +288,8 @@ int attn_fwd_mma_launch(int B, int L, int H, float scale, const void *qkv, void 
         UP3D_CUDA_OK(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         configured = sm;
     }
-    attn_fwd_mma_kernel<<<dim3(div_up(L, AM_QT), H, B), AM_FWD_THREADS, sm, st>>>(L, H, scale, (const bf16 *)qkv, (bf16 *)o, lse);
-    UP3D_LAUNCH_OK("attn_fwd_mma_kernel");
+    UP3D_CUDA_OK(launch_pdl(attn_fwd_mma_kernel, dim3(div_up(L, AM_QT), H, B), dim3(AM_FWD_THREADS), sm, st, L, H, scale,
+                            (const bf16 *)qkv, (bf16 *)o, lse));
     return 0;
 }
 
@@ -297,9 +301,8 @@ int attn_bwd_mma_launch(int B, int L, int H, float scale, const void *qkv, const
         UP3D_CUDA_OK(cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         configured = sm;
     }
-    attn_bwd_mma_kernel<<<dim3(div_up(L, AM_QT), H, B), AM_BWD_THREADS, sm, st>>>(L, H, scale, (const bf16 *)qkv, (const bf16 *)o,
-                                                                                   lse, (const bf16 *)dout, (bf16 *)dqkv);
-    UP3D_LAUNCH_OK("attn_bwd_mma_kernel");
+    UP3D_CUDA_OK(launch_pdl(attn_bwd_mma_kernel, dim3(div_up(L, AM_QT), H, B), dim3(AM_BWD_THREADS), sm, st, L, H, scale,
+                            (const bf16 *)qkv, (const bf16 *)o, lse, (const bf16 *)dout, (bf16 *)dqkv));
     return 0;
 }
 

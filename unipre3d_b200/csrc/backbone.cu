@@ -61,6 +61,8 @@ ln_fwd_kernel(int T, int L, const float *__restrict__ x, const AT *__restrict__ 
               const float *__restrict__ pos, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
               float *__restrict__ xs_out, AT *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out) {
     constexpr int C = 128 * NV;
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     if (row >= T) return;
@@ -120,6 +122,8 @@ ln_bwd_kernel(int T, int L, const AT *__restrict__ dy, const float *__restrict__
               float *__restrict__ dbias) {
     constexpr int C = 128 * NV;
     __shared__ float s_red[LN_WARPS][C];
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 acc_g[NV], acc_b[NV], acc_s[NV];
 #pragma unroll
@@ -204,6 +208,8 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 
 template <typename AT>
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(size_t n4, const AT *__restrict__ x, AT *__restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = Vec4<AT>::load(x + 4 * i);
         Vec4<AT>::store(y + 4 * i, make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w)));
@@ -222,6 +228,8 @@ __global__ void __launch_bounds__(CL_MAX_CT * CL_LANES)
 col_tile_kernel(int T, int L, int Ccols, const void *__restrict__ in0_, const AT *__restrict__ pre,
                 const float *__restrict__ scale, AT *__restrict__ out, float *__restrict__ dbias) {
     __shared__ float4 s_acc[CL_LANES][CL_MAX_CT];
+    pdl_trigger();
+    pdl_wait();
     const int ct = threadIdx.x, lane_r = threadIdx.y;
     const int col = (blockIdx.y * blockDim.x + ct) * 4;
     const bool col_ok = col < Ccols;
@@ -407,16 +415,18 @@ static int launch_ln_fwd(int NV, int T, int L, const float *x, const void *delta
                          const float *gamma, const float *beta, float eps, float *xs, void *y, float *mean, float *rstd,
                          cudaStream_t st) {
     const int grid = div_up(T, LN_WARPS);
+    cudaError_t e = cudaSuccess;
 #define LN_FWD_CASE(N)                                                                                           \
     case N:                                                                                                      \
-        ln_fwd_kernel<AT, N><<<grid, LN_WARPS * 32, 0, st>>>(T, L, x, (const AT *)delta, scale, pos, gamma, beta, eps, xs, \
-                                                              (AT *)y, mean, rstd);                              \
+        e = launch_pdl(ln_fwd_kernel<AT, N>, dim3(grid), dim3(LN_WARPS * 32), 0, st, T, L, x, (const AT *)delta, scale, pos, \
+                       gamma, beta, eps, xs, (AT *)y, mean, rstd);                                               \
         break;
     switch (NV) {
         LN_FWD_CASE(1) LN_FWD_CASE(2) LN_FWD_CASE(3) LN_FWD_CASE(4) LN_FWD_CASE(6) LN_FWD_CASE(8)
         default: return set_error("up3d_ln_fwd: width %d not supported (128 x {1,2,3,4,6,8})", NV * 128);
     }
 #undef LN_FWD_CASE
+    if (e != cudaSuccess) return set_error("launch of ln_fwd_kernel failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -425,16 +435,18 @@ static int launch_ln_bwd(int NV, int T, int L, const void *dy, const float *xs, 
                          const float *gamma, const float *g_res, const float *scale, float *dx, float *dpos, void *dscaled,
                          float *dgamma, float *dbeta, float *dbias, cudaStream_t st) {
     const int grid = min(div_up(T, LN_WARPS), UP3D_NUM_SMS);     // one row per warp (measured faster than two)
+    cudaError_t e = cudaSuccess;
 #define LN_BWD_CASE(N)                                                                                              \
     case N:                                                                                                         \
-        ln_bwd_kernel<AT, N><<<grid, LN_WARPS * 32, 0, st>>>(T, L, (const AT *)dy, xs, mean, rstd, gamma, g_res, scale, dx, \
-                                                              dpos, (AT *)dscaled, dgamma, dbeta, dbias);           \
+        e = launch_pdl(ln_bwd_kernel<AT, N>, dim3(grid), dim3(LN_WARPS * 32), 0, st, T, L, (const AT *)dy, xs, mean, rstd,  \
+                       gamma, g_res, scale, dx, dpos, (AT *)dscaled, dgamma, dbeta, dbias);                         \
         break;
     switch (NV) {
         LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4) LN_BWD_CASE(6) LN_BWD_CASE(8)
         default: return set_error("up3d_ln_bwd: width %d not supported (128 x {1,2,3,4,6,8})", NV * 128);
     }
 #undef LN_BWD_CASE
+    if (e != cudaSuccess) return set_error("launch of ln_bwd_kernel failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -487,9 +499,11 @@ extern "C" int up3d_gelu_fwd(int act_bf16, int64_t n, const void *x, void *y, up
     const size_t n4 = (size_t)n / 4;
     const int grid = (int)min((size_t)UP3D_NUM_SMS * 8, (n4 + 255) / 256);
     if (act_bf16)
-        gelu_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(n4, (const __nv_bfloat16 *)x, (__nv_bfloat16 *)y);
+        UP3D_CUDA_OK(launch_pdl(gelu_fwd_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, n4,
+                                (const __nv_bfloat16 *)x, (__nv_bfloat16 *)y));
     else
-        gelu_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(n4, (const float *)x, (float *)y);
+        UP3D_CUDA_OK(launch_pdl(gelu_fwd_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, n4, (const float *)x,
+                                (float *)y));
     UP3D_LAUNCH_OK("gelu_fwd_kernel");
     return 0;
 }
@@ -502,10 +516,11 @@ static int launch_col_tile(int act_bf16, int T, int L, int C, const void *in0, c
         if ((C / 4) % t == 0) { ct = t; break; }
     const dim3 block(ct, CL_LANES), grid(div_up(T, CL_LANES * CL_U), div_up(C / 4, ct));
     if (act_bf16)
-        col_tile_kernel<__nv_bfloat16, MODE><<<grid, block, 0, st>>>(T, L, C, in0, (const __nv_bfloat16 *)pre, scale,
-                                                                      (__nv_bfloat16 *)out, dbias);
+        UP3D_CUDA_OK(launch_pdl(col_tile_kernel<__nv_bfloat16, MODE>, grid, block, 0, st, T, L, C, in0,
+                                (const __nv_bfloat16 *)pre, scale, (__nv_bfloat16 *)out, dbias));
     else
-        col_tile_kernel<float, MODE><<<grid, block, 0, st>>>(T, L, C, in0, (const float *)pre, scale, (float *)out, dbias);
+        UP3D_CUDA_OK(launch_pdl(col_tile_kernel<float, MODE>, grid, block, 0, st, T, L, C, in0, (const float *)pre, scale,
+                                (float *)out, dbias));
     return 0;
 }
 

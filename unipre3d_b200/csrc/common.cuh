@@ -47,6 +47,31 @@ __device__ __forceinline__ float xfma(float a, float b, float c) { return __fmaf
 __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may begin while its predecessor on
+// the stream is still draining; it must execute pdl_wait() before its first access to memory the predecessor (or any
+// earlier kernel of the stream) touches.  pdl_trigger() lets the NEXT kernel of the stream start its own prologue.
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // UP3D_PDL=0 in the environment or up3d_set_pdl(0) turns the launch attribute off
+
+template <typename... KArgs, typename... CallArgs>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     CallArgs... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -26,7 +26,10 @@ from typing import List, Optional
 import torch
 import torch.nn.functional as F
 
+import os
+
 from . import _lib
+from . import tc_linear as tcl
 from ._lib import check, ptr, require_cuda, stream_ptr
 
 _KEEP_CACHE = {}
@@ -101,6 +104,11 @@ def attn_bwd(qkv, o, lse, do, B, L, H, D, scale, out=None):
     return dqkv
 
 
+def use_tc(act_dtype) -> bool:
+    """bf16 GEMMs go to the hand-written tcgen05 kernel (csrc/gemm_tc.cu); UP3D_TC_LINEAR=0 keeps the library GEMMs."""
+    return act_dtype == torch.bfloat16 and os.environ.get("UP3D_TC_LINEAR", "1") != "0"
+
+
 def _wgrad(dy, x):
     """dW = dy^T @ x written in fp32 by the GEMM itself (no cast pass for the fp32 master gradient)."""
     if dy.dtype == torch.float32:
@@ -116,6 +124,26 @@ def _wgrad_batched(dy, x):
     return torch.bmm(dy.transpose(1, 2), x, out_dtype=torch.float32)
 
 
+def _linear_deep(x, w, b, tc):
+    """y = x W^T + b for the deep-K Linear (fc2: K = 4C)."""
+    if tc and _TC_ALL:
+        return tcl.tc_linear(x, w, b)
+    return F.linear(x, w, b)
+
+
+def _dx_deep(dy, w, tc):
+    """dx = dy W for the Linears whose OUTPUT is wide (qkv: 3C, fc1: 4C), i.e. a deep-K dX product."""
+    if tc and _TC_ALL:
+        return tcl.tc_linear(dy, w, None, b_major=tcl.B_NMAJOR)
+    return dy @ w
+
+
+# Which Linears run on the hand-written tcgen05 kernel (csrc/gemm_tc.cu).  Default: the two whose epilogue absorbs a
+# whole elementwise pass (fc1 + bias + GELU forward; dX of fc2 + GELU backward) -- measured 4.9 us vs 4.0 + 4.5 us and
+# 4.4 us vs 3.9 + 7.3 us per block against library GEMM + separate kernel.  The plain 1032-row GEMMs are L2->SM
+# bandwidth-bound; there the library's 2-CTA multicast kernels are still 0.5-1 us faster per call (tools/bench_tc_linear.py),
+# so they stay on the library unless UP3D_TC_ALL=1.
+_TC_ALL = os.environ.get("UP3D_TC_ALL", "0") != "0"
 _SIDE_STREAMS = {}
 # Data-parallel hook (set by trainer.Trainer when world > 1): called at the end of the stack's backward with the list of
 # its parameter gradients (order = run_encoder_stack's parameter order); returns the tensors autograd should see.  The
@@ -171,6 +199,7 @@ class EncoderStackFn(torch.autograd.Function):
         saved, attn_nodes = [], []
         own_attn = attn_supported(act, L, D)
         Hd = meta.compute_weights[0][3].shape[0]
+        tc = use_tc(act) and tcl.supported(T, C, C) and tcl.supported(T, Hd, C)
         with torch.cuda.device(x.device), torch.autocast("cuda", enabled=False):
             # the A-side operands of the four weight-gradient GEMMs, stacked over the blocks (one batched GEMM each in
             # the backward): LayerNorm outputs, attention outputs, GELU outputs
@@ -182,7 +211,7 @@ class EncoderStackFn(torch.autograd.Function):
                 s1 = masks[2 * i] if masks is not None else None
                 s2 = masks[2 * i + 1] if masks is not None else None
                 xs, y1, mu1, rs1 = ln_fwd(xcur, pend, pend_scale, pos2, n1w, n1b, meta.eps1[i], L, act, y_out=Y1[i])
-                qkv = y1 @ wqkv.t()
+                qkv = tcl.tc_linear(y1, wqkv) if (tc and _TC_ALL) else y1 @ wqkv.t()
                 if own_attn:
                     o, lse = attn_fwd(qkv, B, L, H, D, meta.scale, out=O[i])
                     attn_nodes.append(None)
@@ -194,17 +223,20 @@ class EncoderStackFn(torch.autograd.Function):
                         o_l = o4.transpose(1, 2).reshape(T, C)
                     o, lse = O[i].copy_(o_l.detach()), mu1.new_empty(0)
                     attn_nodes.append((qkv_l, o_l))
-                a = F.linear(o, wproj, bproj)
+                a = tcl.tc_linear(o, wproj, bproj) if (tc and _TC_ALL) else F.linear(o, wproj, bproj)
                 x2, y2, mu2, rs2 = ln_fwd(xs, a, s1, None, n2w, n2b, meta.eps2[i], L, act, y_out=Y2[i])
-                pre = F.linear(y2, w1, b1)
-                h = gelu_fwd(pre, out=HH[i])
-                d = F.linear(h, w2, b2)
+                if tc:      # fc1 + bias + GELU in the GEMM epilogue (pre = the GELU input the backward re-reads)
+                    h, pre = tcl.tc_linear(y2, w1, b1, epilogue=tcl.EPI_GELU, out=HH[i])
+                else:
+                    pre = F.linear(y2, w1, b1)
+                    h = gelu_fwd(pre, out=HH[i])
+                d = _linear_deep(h, w2, b2, tc)
                 saved += [xs, mu1, rs1, x2, mu2, rs2, pre, qkv, lse]
                 xcur, pend, pend_scale = x2, d, s2
             out, _, _, _ = ln_fwd(xcur, pend, pend_scale, None, None, None, 0.0, L, act, want_y=False)
         saved += [Y1, O, Y2, HH]
         ctx.meta, ctx.depth, ctx.attn_nodes, ctx.own_attn = meta, depth, attn_nodes, own_attn
-        ctx.has_masks = masks is not None
+        ctx.has_masks, ctx.tc = masks is not None, tc
         ctx.save_for_backward(*(saved + list(params) + ([masks] if masks is not None else [])))
         return out.view(B, L, C)
 
@@ -220,7 +252,7 @@ class EncoderStackFn(torch.autograd.Function):
         params = sv[n_act:n_act + PARAMS_PER_BLOCK * depth]
         masks = sv[-1] if ctx.has_masks else None
         Hd = meta.compute_weights[0][3].shape[0]
-        dev = gout.device
+        dev, tc = gout.device, ctx.tc
         with torch.cuda.device(dev), torch.autocast("cuda", enabled=False):
             g = gout.reshape(T, C).contiguous().float()
             # all column-sum gradients of the stack in one zero-filled buffer (the kernels accumulate atomically)
@@ -246,25 +278,30 @@ class EncoderStackFn(torch.autograd.Function):
                 s1 = masks[2 * i] if masks is not None else None
                 s2_prev = masks[2 * i - 1] if (masks is not None and i > 0) else None
                 # ---- MLP branch
-                dh = dd @ w2
-                dpre = gelu_bwd(dh, pre, sm(i, 6, Hd), out=DPRE[i])
-                dy2 = dpre @ w1
+                if tc:      # dX of fc2 with the GELU backward in the epilogue; fc1's bias gradient = column sums, below
+                    dpre = tcl.tc_linear(dd, w2, None, b_major=tcl.B_NMAJOR, epilogue=tcl.EPI_GELU_BWD, aux_in=pre, out=DPRE[i])
+                else:
+                    dh = dd @ w2
+                    dpre = gelu_bwd(dh, pre, sm(i, 6, Hd), out=DPRE[i])
+                dy2 = _dx_deep(dpre, w1, tc)
                 dx2, da = ln_bwd(dy2, x2, mu2, rs2, n2w, g, s1, L, None, True, sm(i, 3), sm(i, 4), sm(i, 2),
                                  scaled_out=DA[i])
                 # ---- attention branch
-                do = da @ wproj
+                do = tcl.tc_linear(da, wproj, None, b_major=tcl.B_NMAJOR) if (tc and _TC_ALL) else da @ wproj
                 if ctx.own_attn:
                     dqkv = attn_bwd(qkv, O[i], lse, do, B, L, H, D, meta.scale, out=DQKV[i])
                 else:
                     qkv_l, o_l = ctx.attn_nodes[i]
                     (dqkv,) = torch.autograd.grad(o_l, qkv_l, do)
                     dqkv = DQKV[i].copy_(dqkv)
-                dy1 = dqkv @ wqkv
+                dy1 = _dx_deep(dqkv, wqkv, tc)
                 g, dd = ln_bwd(dy1, xs, mu1, rs1, n1w, dx2, s2_prev, L, dpos, i > 0, sm(i, 0), sm(i, 1),
                                sm(i - 1, 5) if i > 0 else None, scaled_out=DD[i - 1] if i > 0 else None)
             # ---- weight gradients of all blocks: four batched GEMMs (fp32 written by the GEMM)
             gW2, gW1 = _wgrad_batched(DD, HH), _wgrad_batched(DPRE, Y2)
             gWproj, gWqkv = _wgrad_batched(DA, O), _wgrad_batched(DQKV, Y1)
+            if tc:          # fc1 bias gradients of all blocks: one column-sum pass over the stacked dpre
+                small.view(depth, per)[:, 6 * C:].copy_(DPRE.sum(dim=1, dtype=torch.float32))
             for i in range(depth):
                 base = i * PARAMS_PER_BLOCK
                 grads[base + 0], grads[base + 1] = sm(i, 0), sm(i, 1)

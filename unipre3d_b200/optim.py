@@ -100,11 +100,16 @@ class FusedClipAdamW(torch.optim.AdamW):
         self._s_ptrs = i64(sh) if any(sh) else None
         self._g_ptrs = torch.zeros(len(ps), dtype=torch.int64, device=dev)
         self._capture_bufs = [torch.empty(len(ps), dtype=torch.int64).pin_memory() for _ in range(2)]
+        # a fresh (all-zero) gradient-pointer table must be re-uploaded even when the gradients kept their addresses
+        # (data-parallel mode: every p.grad is a fixed view of GradSync's flat buffer)
+        self._last_ptrs = None
+        self._ring, self._ring_ev, self._ring_i = [], [], 0
         self._built = True
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._built = False                    # moments were replaced: rebuild the pointer tables at the next step
+        self._last_ptrs = None                 # ... and re-upload the gradient pointers into the new table
 
     def _upload_grad_ptrs(self) -> None:
         """The gradient tensors are re-allocated by autograd every step (at fixed graph-pool addresses under CUDA-graph

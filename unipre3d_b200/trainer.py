@@ -151,10 +151,16 @@ class ModelManager:
                     g["lr"] = g["lr"] * self.lr_gamma
 
     def save_checkpoint(self, iteration: int, best_psnr: float, save_path: str) -> None:
-        """Same dict keys as train_network.py:200-210."""
-        torch.save({"iteration": iteration, "optimizer_state_dict": self.optimizer.state_dict(),
-                    "model_state_dict": (self.ema.ema_model.state_dict() if self.ema else self.model.state_dict()),
-                    "best_PSNR": best_psnr}, save_path)
+        """Same dict keys as train_network.py:200-210 (`model_state_dict` holds the EMA weights when EMA is on, as in
+        the reference) plus what an exact resume needs and the reference drops: the online weights the Adam moments
+        belong to and the EMA schedule position."""
+        ckpt = {"iteration": iteration, "optimizer_state_dict": self.optimizer.state_dict(),
+                "model_state_dict": (self.ema.ema_model.state_dict() if self.ema else self.model.state_dict()),
+                "best_PSNR": best_psnr}
+        if self.ema:
+            ckpt["online_model_state_dict"] = self.model.state_dict()
+            ckpt["ema_state"] = {"step": self.ema.step, "initted": self.ema.initted}
+        torch.save(ckpt, save_path)
 
     def save_latest_checkpoint(self, iteration: int, best_psnr: float, save_dir: str) -> None:
         """train_network.py:212-215."""
@@ -168,14 +174,31 @@ class ModelManager:
         """Resume from a checkpoint written by `save_checkpoint` (or by the reference's ModelManager: same keys).
         Frozen image-network weights absent from the file keep their current values."""
         ckpt = torch.load(path, map_location=self.device)
-        info = self.model.load_state_dict(ckpt["model_state_dict"], strict=False)
+
+        def clean(sd):
+            # a reference checkpoint may come from a DDP-wrapped model ("module." prefix) and always carries the frozen
+            # AutoencoderKL under image_network.* (a submodule there; absent here unless model.image_branch=sdvae)
+            sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+            own = set(self.model.state_dict().keys())
+            return {k: v for k, v in sd.items() if k in own or not k.startswith("image_network.")}
+
+        ema_sd = clean(ckpt["model_state_dict"])
+        online_sd = clean(ckpt["online_model_state_dict"]) if "online_model_state_dict" in ckpt else ema_sd
+        info = self.model.load_state_dict(online_sd, strict=False)
         bad = [k for k in info.missing_keys if not k.startswith("image_network.")] + list(info.unexpected_keys)
         if bad:
             raise RuntimeError(f"checkpoint does not match the model: {bad[:8]}")
         if self.ema:
-            self.ema.ema_model.load_state_dict(ckpt["model_state_dict"], strict=False)
+            self.ema.ema_model.load_state_dict(ema_sd, strict=False)
+            st = ckpt.get("ema_state")
+            if st is not None:
+                self.ema.step, self.ema.initted = int(st["step"]), bool(st["initted"])
+            else:       # reference checkpoint: the EMA weights ARE the saved model; continue its schedule from `iteration`
+                self.ema.step, self.ema.initted = int(ckpt.get("iteration", 0)), True
         if load_optimizer and "optimizer_state_dict" in ckpt:
             self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+            # StepLR phase: the decayed lr was just loaded, keep counting from the saved iteration (train_network.py:160-163)
+            self._sched_step = int(ckpt.get("iteration", 0))
         for m in self.model.modules():          # bf16 weight shadows (mixed_precision.ShadowWeights) follow the masters
             w16 = getattr(m, "_w16", None)
             if w16 is not None:
@@ -240,6 +263,11 @@ class Trainer:
         self.iteration = 0
         self._graph = None
         self._static: Optional[dict] = None
+        if self._lpips_due(int(getattr(cfg.opt, "iterations", 0))):
+            import warnings
+            warnings.warn(f"opt.lambda_lpips={cfg.opt.lambda_lpips} switches the LPIPS-VGG term on after iteration "
+                          f"{cfg.opt.start_lpips_after}; its pretrained weights are not shipped, so train_iteration "
+                          f"raises there (set opt.lambda_lpips=0 to train without it)", stacklevel=2)
         self._loss_buf = torch.zeros((), dtype=torch.float32, device=self.device)
         self._loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -247,6 +275,18 @@ class Trainer:
         # input pipelining: the next batch is copied host->device on a side stream while the current step runs
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._staged = None          # (key, device dict, ready event)
+
+    def _lpips_due(self, iteration: int) -> bool:
+        """train_network.py:229-231, 288-296: the LPIPS term joins the loss after opt.start_lpips_after."""
+        return self.cfg.opt.lambda_lpips != 0 and iteration > self.cfg.opt.start_lpips_after
+
+    def load_checkpoint(self, path: str, load_optimizer: bool = True) -> Dict[str, float]:
+        """ModelManager.load_checkpoint + everything of the step that holds pointers into the replaced state: the
+        captured graph (parameter / moment / pointer tables) is dropped and re-captured at the next iteration."""
+        info = self.model_manager.load_checkpoint(path, load_optimizer=load_optimizer)
+        self.iteration = info["iteration"]
+        self._graph, self._static, self._staged = None, None, None
+        return info
 
     # ---------------------------------------------------------------------------------------------
     def render_validation_views(self, gaussian_splats, data) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -315,6 +355,40 @@ class Trainer:
         self._clip_and_step()
         return loss
 
+    @torch.no_grad()
+    def _snapshot_state(self):
+        m, opt = self.model_manager.model, self.model_manager.optimizer
+        tens = list(m.parameters()) + list(m.buffers())
+        had_state = bool(getattr(opt, "_built", False))
+        moments = [(opt.state[p]["exp_avg"].clone(), opt.state[p]["exp_avg_sq"].clone())
+                   for p in self.params] if had_state else None
+        return {"tens": [t.detach().clone() for t in tens], "moments": moments,
+                "opt_state": opt._state.clone() if had_state else None}
+
+    @torch.no_grad()
+    def _restore_state(self, snap) -> None:
+        m, opt = self.model_manager.model, self.model_manager.optimizer
+        for t, s in zip(list(m.parameters()) + list(m.buffers()), snap["tens"]):
+            t.copy_(s)
+        for p in self.params:
+            st = opt.state.get(p)
+            if not st or "exp_avg" not in st:
+                continue
+            if snap["moments"] is None:
+                st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+        if snap["moments"] is not None:
+            for p, (a, b) in zip(self.params, snap["moments"]):
+                opt.state[p]["exp_avg"].copy_(a); opt.state[p]["exp_avg_sq"].copy_(b)
+            opt._state.copy_(snap["opt_state"])
+        elif getattr(opt, "_built", False):
+            opt._state.zero_()
+        for mod in m.modules():          # bf16 weight shadows follow the restored masters
+            w16 = getattr(mod, "_w16", None)
+            if w16 is not None:
+                w16.copy_(mod.weight.detach().reshape(w16.shape))
+                if getattr(mod, "_b16", None) is not None:
+                    mod._b16.copy_(mod.bias.detach())
+
     # ---------------------------------------------------------------------------------------------
     def _copy_into_static(self, data) -> None:
         def cp(dst, src):
@@ -355,6 +429,9 @@ class Trainer:
         step's host batch; its H2D copy is overlapped with this step's compute."""
         self.iteration += 1
         mm = self.model_manager
+        if self._lpips_due(self.iteration):
+            # evaluated on the host EVERY iteration: a captured graph would otherwise keep replaying the LPIPS-free loss
+            raise NotImplementedError("LPIPS loss needs VGG weights (not shipped); set opt.lambda_lpips=0")
         if not self.use_cuda_graph:
             dev = self._take_staged(data)
             if prefetch is not None:
@@ -363,7 +440,11 @@ class Trainer:
         else:
             if self._static is None:
                 self._static = _to_device(data, self.device, non_blocking=False)
-                # warm-up on a side stream (allocator, cuBLAS handles, layout cache, lazy grads), then capture
+                # warm-up on a side stream (allocator, cuBLAS handles, layout cache, lazy grads), then capture.  The
+                # warm-up steps are real optimizer steps on the first batch: model, BatchNorm buffers, optimizer
+                # moments and the step counter are snapshotted and put back, so iteration 1 starts from the same state
+                # as in eager mode (only the RNG stream has advanced).
+                snap = self._snapshot_state()
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
@@ -371,6 +452,7 @@ class Trainer:
                         self._step_body(self._static)
                 torch.cuda.current_stream().wait_stream(s)
                 torch.cuda.synchronize()
+                self._restore_state(snap)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
                     self._loss_buf.copy_(self._step_body(self._static))
