@@ -255,7 +255,8 @@ def test_checkpoint_round_trip_keeps_reference_keys(tmp_path):
     a = ModelManager(cfg, torch.device("cpu"))
     a.save_latest_checkpoint(123, 21.5, str(tmp_path))
     ck = torch.load(tmp_path / "model_latest.pth")
-    assert set(ck) == {"iteration", "optimizer_state_dict", "model_state_dict", "best_PSNR"}
+    ref_keys = {"iteration", "optimizer_state_dict", "model_state_dict", "best_PSNR"}      # train_network.py:200-210
+    assert ref_keys <= set(ck) and set(ck) - ref_keys <= {"online_model_state_dict", "ema_state"}
     assert any(k.startswith("point_network.encoder.blocks.blocks.0.attn.qkv") for k in ck["model_state_dict"])
     torch.manual_seed(1)
     b = ModelManager(cfg, torch.device("cpu"))
@@ -264,3 +265,14 @@ def test_checkpoint_round_trip_keeps_reference_keys(tmp_path):
     assert meta == {"iteration": 123, "best_PSNR": 21.5}
     for (ka, pa), (kb, pb) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
         assert ka == kb and torch.equal(pa, pb), ka
+    assert b._sched_step == 123                                       # StepLR phase follows the saved iteration
+    if b.ema is not None:
+        assert (b.ema.step, b.ema.initted) == (a.ema.step, a.ema.initted)
+    # a checkpoint as the REFERENCE writes it: DDP "module." prefix, frozen AutoencoderKL under image_network.*, no extras
+    ref_ck = {"iteration": 7, "best_PSNR": 1.0, "optimizer_state_dict": ck["optimizer_state_dict"],
+              "model_state_dict": {**{"module." + k: v for k, v in ck["model_state_dict"].items()},
+                                   "module.image_network.encoder.conv_in.weight": torch.zeros(2, 2)}}
+    torch.save(ref_ck, tmp_path / "ref_style.pth")
+    c = ModelManager(cfg, torch.device("cpu"))
+    assert c.load_checkpoint(str(tmp_path / "ref_style.pth")) == {"iteration": 7, "best_PSNR": 1.0}
+    assert c._sched_step == 7 and (c.ema is None or (c.ema.step == 7 and c.ema.initted))

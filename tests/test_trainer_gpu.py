@@ -86,10 +86,13 @@ def test_cuda_graph_step_matches_eager_and_learns():
             if blk.__class__.__name__ == "DropPath":
                 blk.drop_prob = 0.0
         losses[mode] = [tr.train_iteration(data) for _ in range(6)]
-    # graph mode runs 3 warm-up steps on the same batch before capture, so compare its first loss with eager step 4
+    # graph mode's warm-up steps are rolled back (parameters, BatchNorm buffers, moments, step counter), so the two
+    # trajectories coincide step for step (float atomics in the raster backward leave ~1e-6 relative noise)
     assert np.isfinite(losses[True]).all() and np.isfinite(losses[False]).all()
     assert losses[False][-1] < losses[False][0], "eager loss does not decrease"
-    assert abs(losses[True][0] - losses[False][3]) <= 5e-3 * abs(losses[False][3]) + 1e-5
+    for a, b in zip(losses[True], losses[False]):
+        assert abs(a - b) <= 2e-3 * abs(b) + 1e-5, (losses[True], losses[False])
+    assert abs(losses[True][0] - losses[False][0]) <= 1e-5 * abs(losses[False][0]) + 1e-7
 
 
 def test_lazy_image_features_equal_dense_dataflow():

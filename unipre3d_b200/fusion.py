@@ -128,8 +128,10 @@ class FeatureFusion:
                 and N <= FUSED_MAX_POINTS and not FORCE_MODULE_PATH):
             keep, mapped, _ = fused_project_and_sample(image_features, center, c2w_projection_matrix, intrinsic)
             return self._fuse(x, center, keep, mapped, C)
-        with torch.no_grad():
-            pi_xy, p_depth = self.project_points_to_image(center, c2w_projection_matrix, intrinsic)
+        # geometry stays fp32 whatever the autocast state: a bf16 projection lands on different pixels (the reference has
+        # no mixed precision anywhere)
+        with torch.no_grad(), torch.autocast(center.device.type, enabled=False):
+            pi_xy, p_depth = self.project_points_to_image(center.float(), c2w_projection_matrix.float(), intrinsic)
             fx, fy = pi_xy[..., 0], pi_xy[..., 1]
             # NaN-safe: comparisons with NaN are False, as in the reference after .long() of a finite value
             inside = (fx >= 0) & (fy >= 0) & (fx < H) & (fy < W) & (p_depth >= 0)
