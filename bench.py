@@ -155,17 +155,55 @@ def run_cpu_port(args, as_reference: bool, budget_s: float = 25.0):
             "ms_per_step": dt * 1e3, "steps": steps, "warmup": warm}
 
 
+def run_reference_modules(steps: int, warm: int, n_objects: int, budget_s: float):
+    """The reference's OWN backbone modules (staged into oracle/_ref/pyref by build()) on the host cores, fp32, all
+    threads; tokenizer kernels and rasterizer = the CPU restatements (the reference has no CPU path for either).
+    No unipre3d_b200 import on this path."""
+    from oracle import oracle_lib, ref_step
+    oracle_lib.build()
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = ref_step.RefStepper(n_objects=n_objects)
+    t0 = time.perf_counter()
+    for _ in range(max(warm, 1)):
+        st.step()
+    per = (time.perf_counter() - t0) / max(warm, 1)
+    steps = max(1, min(steps, int(budget_s / max(per, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st.step()
+    dt = (time.perf_counter() - t0) / steps
+    cores = max(torch.get_num_threads(), oracle_lib.num_threads())
+    return {"value": st.n_views() / dt, "unit": "views/s", "cores": cores, "kind": "reference",
+            "sample": f"{n_objects} of {OBJECTS_PER_GPU} objects x 4 views per step (8192 pts -> 128 Gaussians, 256x256), "
+                      f"{steps} timed steps after {max(warm, 1)} warm-up; backbone = the reference's own "
+                      "PointTransformerEncoder + FeatureFusion modules (oracle/_ref/pyref, unmodified files) + dense "
+                      "image_conv on N(0,1) decoder features, torch CPU fp32; FPS/ball-query/group and the rasterizer = "
+                      "C/OpenMP restatements (the reference has no CPU path for them)",
+            "ms_per_step": dt * 1e3, "steps": steps, "warmup": max(warm, 1)}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = run_cpu_port(args, as_reference=True)
+    same_config = False
+    try:
+        from oracle import ref_step
+        if not ref_step.available():
+            raise RuntimeError("oracle/_ref/pyref not staged")
+        cb = run_reference_modules(args.steps, min(args.warmup, 2), OBJECTS_PER_GPU, budget_s=150.0)
+        same_config = True
+    except Exception as e:      # the staged reference files are absent: fall back to the self-contained CPU port
+        print(f"[bench] reference modules unavailable ({e!r}); using the CPU port", file=sys.stderr)
+        cb = run_cpu_port(args, as_reference=True)
     line = {"impl": "reference", "metric": "views/sec (8192 pts->256^2 render), full pre-training step",
             "value": cb["value"], "unit": "views/s", "n_gpus": args.gpus, "steps": cb["steps"], "warmup": cb["warmup"],
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "transformer_pretraining, 8 objects x 4 views, 8192 pts, 256x256 (bounded sample: "
-                                   "1 object x 4 views per step)", "l2": "n/a (CPU)"},
+            "config": {"workload": "transformer_pretraining: 8 objects x 4 rendered views per GPU, 8192-pt clouds, "
+                                   "256x256, 128 Gaussians/object, SH degree 1 (BASELINE.json configs[1])"
+                                   + ("" if same_config else " (bounded sample: 1 object x 4 views per step)"),
+                       "l2": "n/a (CPU)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -184,6 +222,9 @@ def raster_roofline(trainer, batch_dev, cfg, reps: int, peaks, peak_kind):
     buf = (C.c_float * 6)()
     try:
         for r in range(reps):
+            # keep the GPU busy (~50 ms spin) while the host enqueues the whole eager step, so that no kernel waits for
+            # its launch: the event pairs around the raster kernels then bracket device time only
+            torch.cuda._sleep(100_000_000)
             trainer._forward_backward(batch_dev)          # eager forward + render + loss + backward (autocast as the step)
             _lib.check(_lib.lib.up3d_raster_timing_read(buf))
             ms[r] = list(buf)
@@ -242,6 +283,7 @@ def raster_only_headline(device, reps: int, peaks):
     _lib.check(_lib.lib.up3d_raster_timing_enable(1))
     try:
         for r in range(reps + 3):
+            torch.cuda._sleep(20_000_000)                  # host runs ahead of the device (see raster_roofline)
             color, _, _ = rasterize_batch(cat["means3D"], cat["opacities"], cat["scales"], cat["rotations"], vm, pm, cp,
                                           bg, **kw)
             color.backward(w)
@@ -260,6 +302,62 @@ def raster_only_headline(device, reps: int, peaks):
             "reference_algorithm_bytes": ref_bytes,
             "effective_GBs_vs_reference_traffic": ref_bytes / (tot * 1e-3) / 1e9,
             "frac_of_hbm_peak_vs_reference_traffic": ref_bytes / (tot * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
+
+def legacy_gpu_pointops(device, reps: int = 20):
+    """the reference's OWN pointnet2_batch kernels (oracle/_ref/pointnet2_batch_cuda.so, compiled unmodified
+    for sm_100 by oracle/build_ref.py) timed on this GPU next to the kernels that replace them, at the tokenizer's size
+    (8 clouds x 8192 points -> 128 centres, 32 neighbours, radius 0.1).  CUDA events, L2-resident inputs (96 KB/cloud)."""
+    import importlib.util
+    from unipre3d_b200.pointops import furthest_point_sample, subsample_group
+    so = os.path.join(ROOT, "oracle", "_ref", "pointnet2_batch_cuda.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/pointnet2_batch_cuda.so not built"}
+    spec = importlib.util.spec_from_file_location("pointnet2_batch_cuda", so)
+    ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ext)
+    B, N, M, K, r = OBJECTS_PER_GPU, N_POINTS, 128, 32, 0.1
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = (torch.randn(B, N, 3, generator=g) * 0.2).to(device).contiguous()
+    xt = x.transpose(1, 2).contiguous()
+
+    def ev_time(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    idx = torch.empty(B, M, dtype=torch.int32, device=device)
+    temp = torch.empty(B, N, dtype=torch.float32, device=device)
+    nidx = torch.empty(B, M, K, dtype=torch.int32, device=device)
+    grouped = torch.empty(B, 3, M, K, dtype=torch.float32, device=device)
+
+    def ref_fps():
+        temp.fill_(1e10)                              # subsample.py:93 (the reference re-creates it per call)
+        ext.furthest_point_sampling_wrapper(B, N, M, x, temp, idx)
+
+    ref_fps()
+    center = torch.gather(x, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+
+    def ref_group():
+        ext.ball_query_wrapper(B, N, M, r, K, center, x, nidx)
+        ext.group_points_wrapper(B, 3, N, M, K, xt, nidx, grouped)
+
+    out = {"shape": f"B={B} N={N} centres={M} K={K} radius={r}",
+           "reference_fps_us": ev_time(ref_fps), "up3d_fps_us": ev_time(lambda: furthest_point_sample(x, M)),
+           "reference_ballquery_group_us": ev_time(ref_group),
+           "up3d_subsample_group_us": ev_time(lambda: subsample_group(x, M, K, r)),
+           "note": "up3d_subsample_group = FPS + ball query + grouping + centring in 2 launches (includes the FPS time); "
+                   "the reference needs FPS + gather + ball query + grouping + subtraction"}
+    # index-for-index agreement of the two implementations at this size
+    out["fps_indices_equal"] = bool(torch.equal(furthest_point_sample(x, M), idx))
+    return out
 
 
 def ours(args):
@@ -393,10 +491,18 @@ def ours(args):
         cpu_baseline = None
         if n_gpus == 1 and not args.no_cpu_baseline:
             try:
-                cb = run_cpu_port(args, as_reference=False)
+                from oracle import ref_step
+                if ref_step.available():
+                    cb = run_reference_modules(3, 1, 2, budget_s=20.0)      # bounded sample: 2 objects per step
+                else:
+                    cb = run_cpu_port(args, as_reference=False)
                 cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:
                 cpu_baseline = {"error": repr(e)}
+            try:
+                extra["legacy_gpu_pointops"] = legacy_gpu_pointops(device)
+            except Exception as e:
+                extra["legacy_gpu_pointops_error"] = repr(e)
         value = views_per_step / (ms_resident / args.steps * 1e-3)
         e2e = views_per_step / (ms_e2e / args.steps * 1e-3)
         line = {"metric": "views/sec (8192 pts->256^2 render), full pre-training step", "value": value,

@@ -169,6 +169,8 @@ UP3D_API int up3d_raster_debug_tile_lists(const up3d_raster_desc *d, const void 
  * on the launching stream around each kernel (do not enable while capturing a CUDA graph).  read() blocks on the
  * last event and returns milliseconds for [project, depth_sort, blend_forward, grad-clear, blend_backward,
  * geometry_backward] of the most recent forward / backward on this host thread (-1 where not recorded). */
+/* (diagnostic, process-wide: while enabled only ONE stream may issue raster calls; untimed callers on other streams
+ *  stay correct but are not measured.  All other entry points are thread-safe for distinct streams.) */
 UP3D_API int up3d_raster_timing_enable(int enable);
 UP3D_API int up3d_raster_timing_read(float *ms6);
 

@@ -182,7 +182,17 @@ def test_bench_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "views/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["n_gpus"] == 1 and d["steps"] >= 1 and d["gpu_launches"] == 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference": the reference's own backbone modules staged under oracle/_ref/pyref; "port" when they are absent
+    staged = os.path.exists(os.path.join(root, "oracle", "_ref", "pyref", "bench_batch.npz"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the reference arm must not map the product into its process
+    probe = subprocess.run([sys.executable, "-c", "import sys; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','1'];"
+                            "import runpy; runpy.run_path('bench.py', run_name='__main__');"
+                            "bad=[m for m in sys.modules if m.startswith('unipre3d_b200')]; print('PRODUCT_MODULES', bad)"],
+                           capture_output=True, text=True, timeout=600, cwd=root)
+    if staged:
+        assert "PRODUCT_MODULES []" in probe.stdout, probe.stdout[-500:] + probe.stderr[-500:]
     assert d["e2e"] == {"value": d["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 

@@ -26,6 +26,8 @@
 //                order and writes dL/d{xyz, scale, rot, opacity, SH}.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace up3d {
@@ -1110,15 +1112,29 @@ static int validate_desc(const up3d_raster_desc *d) {
 
 // Optional per-kernel timing with CUDA events recorded on the launching stream (bench.py's roofline leg).
 // Slots: 0 project, 1 depth_sort, 2 blend_forward, 3 gacc clear, 4 blend_backward, 5 geometry_backward.
+// A DIAGNOSTIC facility, process-wide by design (autograd runs the backward on its own host thread, so the state cannot
+// be thread-local): while it is enabled, only ONE stream may issue raster calls; flags are atomics so that concurrent
+// untimed callers on other streams are merely not measured.  Every kernel sits between its own two event records with
+// nothing but its launch in between (function attributes are configured once, ahead of time).
 struct Timing {
-    bool enabled = false, created = false;
+    std::atomic<bool> enabled{false}, fwd_valid{false}, bwd_valid{false};
+    bool created = false;
     cudaEvent_t ev[8];
-    bool fwd_valid = false, bwd_valid = false;
 };
-static Timing g_timing;  // process-wide: autograd runs the backward on its own host thread
+static Timing g_timing;
 static inline void tick(int i, cudaStream_t s) {
-    if (g_timing.enabled) cudaEventRecord(g_timing.ev[i], s);
+    if (g_timing.enabled.load(std::memory_order_relaxed)) cudaEventRecord(g_timing.ev[i], s);
 }
+
+// cudaFuncSetAttribute once per growth of the requirement (not on every call; idempotent under races)
+static int ensure_dyn_smem(const void *fn, std::atomic<size_t> &configured, size_t bytes) {
+    if (bytes <= configured.load(std::memory_order_acquire)) return 0;
+    UP3D_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    size_t cur = configured.load(std::memory_order_relaxed);
+    while (cur < bytes && !configured.compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+    return 0;
+}
+static std::atomic<size_t> g_sort_smem{0}, g_bwd_smem{0};
 
 static ViewConst make_view_const(const up3d_raster_desc *d) {
     ViewConst vc;
@@ -1175,12 +1191,13 @@ int up3d_raster_forward(const up3d_raster_desc *d, const float *means3D, const f
         project_kernel<<<dim3(div_up(d->max_set_size, 256), V), 256, 0, stream>>>(pa);
         UP3D_LAUNCH_OK("project_kernel");
     }
+    SortArgs sa{d->view_rec_start, st, sc, d->max_set_size <= SORT_SMEM_MAX_KEYS ? 1 : 0};
+    size_t sort_smem = SORT_FIXED_SMEM;
+    if (sa.use_smem) sort_smem += (size_t)((d->max_set_size + 3) & ~3) * 16;
+    if (ensure_dyn_smem((const void *)depth_sort_kernel, g_sort_smem, sort_smem)) return 1;
     tick(1, stream);
     {
-        SortArgs sa{d->view_rec_start, st, sc, d->max_set_size <= SORT_SMEM_MAX_KEYS ? 1 : 0};
-        size_t smem = SORT_FIXED_SMEM;
-        if (sa.use_smem) smem += (size_t)((d->max_set_size + 3) & ~3) * 16;
-        UP3D_CUDA_OK(cudaFuncSetAttribute(depth_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = sort_smem;
         depth_sort_kernel<<<V, SORT_THREADS, smem, stream>>>(sa);
         UP3D_LAUNCH_OK("depth_sort_kernel");
     }
@@ -1191,7 +1208,7 @@ int up3d_raster_forward(const up3d_raster_desc *d, const float *means3D, const f
         UP3D_LAUNCH_OK("blend_forward_kernel");
     }
     tick(3, stream);
-    g_timing.fwd_valid = g_timing.enabled;
+    g_timing.fwd_valid = g_timing.enabled.load();
     return 0;
 }
 
@@ -1213,12 +1230,12 @@ int up3d_raster_backward(const up3d_raster_desc *d, const float *means3D, const 
     Scratch sc = carve_scratch(d, scratch);
     const ViewConst vc = make_view_const(d);
     const int V = d->n_views;
+    if (ensure_dyn_smem((const void *)blend_backward_kernel, g_bwd_smem, sizeof(BwdSmem))) return 1;
     tick(4, stream);
     UP3D_CUDA_OK(cudaMemsetAsync(sc.gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)d->n_records, stream));
     tick(5, stream);
     if (V > 0) {
         BlendBwdArgs ba{d->width, d->height, d->view_rec_start, bg, dL_dcolor, sc.gacc, st};
-        UP3D_CUDA_OK(cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
         blend_backward_kernel<<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, sizeof(BwdSmem), stream>>>(ba);
         UP3D_LAUNCH_OK("blend_backward_kernel");
     }
@@ -1233,7 +1250,7 @@ int up3d_raster_backward(const up3d_raster_desc *d, const float *means3D, const 
         UP3D_LAUNCH_OK("geometry_backward_kernel");
     }
     tick(7, stream);
-    g_timing.bwd_valid = g_timing.enabled;
+    g_timing.bwd_valid = g_timing.enabled.load();
     return 0;
 }
 
@@ -1243,7 +1260,8 @@ int up3d_raster_timing_enable(int enable) {
         g_timing.created = true;
     }
     g_timing.enabled = enable != 0;
-    g_timing.fwd_valid = g_timing.bwd_valid = false;
+    g_timing.fwd_valid = false;
+    g_timing.bwd_valid = false;
     return 0;
 }
 
