@@ -30,7 +30,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OBJECTS_PER_GPU, N_POINTS, RES = 8, 8192, 256
+CFG_NAME, GAUSSIANS_PER_OBJECT = "transformer_pretraining", 128
 HBM_FALLBACK_GBS = 6650.0
+
+
+def select_config(name: str) -> None:
+    """--config transformer: BASELINE.json configs[1] (the headline, default).  --config pointmlp: configs[2] per GPU
+    (pointmlp_pretraining, 4 objects x 4 views, 8192 pts -> 8192 Gaussians per object, 256x256)."""
+    global OBJECTS_PER_GPU, CFG_NAME, GAUSSIANS_PER_OBJECT
+    if name == "pointmlp":
+        OBJECTS_PER_GPU, CFG_NAME, GAUSSIANS_PER_OBJECT = 4, "pointmlp_pretraining", N_POINTS
 
 
 def measured_peaks():
@@ -120,7 +129,7 @@ def make_cfg(n_gpus: int):
     ov = [f"data.training_resolution={RES}", f"opt.batch_size={OBJECTS_PER_GPU * n_gpus}"]
     if n_gpus > 1:
         ov.append("general.device=[" + ",".join(str(i) for i in range(n_gpus)) + "]")
-    return compose(overrides=ov)
+    return compose(CFG_NAME, overrides=ov)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -235,7 +244,7 @@ def raster_roofline(trainer, batch_dev, cfg, reps: int, peaks, peak_kind):
     names = ["project", "depth_sort", "blend_forward", "grad_clear", "blend_backward", "geometry_backward"]
     mean = ms.mean(0)
     V = OBJECTS_PER_GPU * int(cfg.opt.imgs_per_obj)
-    P, HW, M = 128 * int(cfg.data.input_images), RES * RES, 4     # Gaussians per object: 128 tokens x input views
+    P, HW, M = GAUSSIANS_PER_OBJECT * int(cfg.data.input_images), RES * RES, 4     # Gaussians per object (x input views)
     # algorithmic bytes of blend_backward per launch (DESIGN.md "Kernels"): depth-ordered records read once per view
     # (48 B each), per-pixel final_T / n_contrib / dL_dcolor (20 B), per-record 9-float partials read-modify-write
     bwd_bytes = V * (P * 48 + HW * 20 + P * 9 * 4 * 2)
@@ -261,14 +270,15 @@ def raster_roofline(trainer, batch_dev, cfg, reps: int, peaks, peak_kind):
     }
 
 
-def raster_only_headline(device, reps: int, peaks):
-    """Raster stage alone at the headline Gaussian count (P = 8192 per object, the pointMLP-true case of SURVEY §8d)."""
+def raster_only_headline(device, reps: int, peaks, regime: str = "reference", B: int = 8, V: int = 4, P: int = 8192,
+                         RES: int = 256):
+    """Raster stage alone: by default at the headline Gaussian count (P = 8192 per object, dense reference regime, the
+    pointMLP-true case of SURVEY §8d); `regime="small"` = the small-splat distribution SURVEY §8d asks to report
+    separately (sort-light / blend-heavy; no HBM fraction is quoted for it)."""
     from unipre3d_b200 import _lib
     from unipre3d_b200.rasterizer import rasterize_batch
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from tests.helpers import make_camera, make_gaussians
-    B, V, P = OBJECTS_PER_GPU, 4, 8192
-    gs = [make_gaussians(P, seed=100 + i, regime="reference") for i in range(B)]
+    from unipre3d_b200.synthetic import make_camera, make_gaussians
+    gs = [make_gaussians(P, seed=100 + i, regime=regime) for i in range(B)]
     cat = {k: torch.tensor(np.concatenate([g[k] for g in gs], 0), device=device).requires_grad_(True) for k in gs[0]}
     cams = [make_camera(az=360.0 * i / (B * V), el=5 + 2.0 * i) for i in range(B * V)]
     vm = torch.tensor(np.stack([c["view"] for c in cams]), device=device)
@@ -293,6 +303,21 @@ def raster_only_headline(device, reps: int, peaks):
     finally:
         _lib.check(_lib.lib.up3d_raster_timing_enable(0))
     tot = float(ms.mean(0).sum())
+    if regime != "reference":
+        from unipre3d_b200.rasterizer import debug_forward_state
+        dbg = debug_forward_state(cat["means3D"].detach(), cat["opacities"].detach(), cat["scales"].detach(),
+                                  cat["rotations"].detach(), vm, pm, cp, bg, set_sizes=[P] * B, views_per_set=[V] * B,
+                                  image_height=RES, image_width=RES, tanfovx=cams[0]["tanfovx"], tanfovy=cams[0]["tanfovy"],
+                                  sh_degree=1, shs=cat["shs"].detach(), tile_lists=True)
+        I_total = int(dbg["tile_counts"].sum().item())
+        return {"workload": f"{B} objects x {V} views, P={P} Gaussians/object (small-splat regime), {RES}x{RES}, fwd+bwd",
+                "ms": tot, "views_per_s": B * V / (tot * 1e-3),
+                "kernels_ms": {n: float(v) for n, v in zip(["project", "depth_sort(+bins)", "blend_forward", "grad_clear",
+                                                             "blend_backward", "geometry_backward"], ms.mean(0))},
+                "num_rendered_I": I_total, "instances_per_s": I_total / (tot * 1e-3),
+                "binned_views": int(dbg["bin_mode"].sum().item()), "views": B * V,
+                "bin_entries_per_visible_record": float(dbg["bin_total"].sum().item()) / max(1, int(dbg["n_visible"].sum().item())),
+                "note": "blend-bound (exp / compositing arithmetic per (pixel, entry)); no HBM fraction is quoted for this regime"}
     I = P * (RES * RES // 256)
     ref_bytes = B * V * (P * (240 + 36 * 4) + 108 * I + 40 * RES * RES)
     return {"workload": f"{B} objects x {V} views, P=8192 Gaussians/object (reference scale regime), 256x256, fwd+bwd",
@@ -486,10 +511,13 @@ def ours(args):
     if rank == 0:
         try:
             extra["raster_only"] = raster_only_headline(device, 5, peaks)
+            extra["raster_only_small_splat"] = raster_only_headline(device, 5, peaks, regime="small")
+            # BASELINE configs[3]-shaped raster stress: one scene of 100k small Gaussians, 4 views of 512x512 (1024 tiles)
+            extra["raster_only_scene_100k"] = raster_only_headline(device, 3, peaks, regime="small", B=1, V=4, P=100000, RES=512)
         except Exception as e:
             extra["raster_only_error"] = repr(e)
         cpu_baseline = None
-        if n_gpus == 1 and not args.no_cpu_baseline:
+        if n_gpus == 1 and not args.no_cpu_baseline and CFG_NAME.startswith("transformer"):
             try:
                 from oracle import ref_step
                 if ref_step.available():
@@ -511,8 +539,9 @@ def ours(args):
                 "vs_baseline": None,
                 "dtype": "f32 rasterizer/point ops/loss/optimizer; backbone GEMMs " + ("f32" if args.fp32 else "bf16 (fp32 accumulate, fp32 master weights)"),
                 "data": "synthetic",
-                "config": {"workload": "transformer_pretraining: 8 objects x 4 rendered views per GPU, 8192-pt clouds, "
-                                       "256x256, 128 Gaussians/object, SH degree 1 (BASELINE.json configs[1])",
+                "config": {"workload": f"{CFG_NAME}: {OBJECTS_PER_GPU} objects x 4 rendered views per GPU, 8192-pt clouds, "
+                                       f"256x256, {GAUSSIANS_PER_OBJECT} Gaussians/object, SH degree 1 (BASELINE.json "
+                                       + ("configs[1])" if CFG_NAME.startswith("transformer") else "configs[2], per-GPU share)"),
                            "objects_per_gpu": OBJECTS_PER_GPU, "views_per_step": views_per_step, "parallelism": f"dp{n_gpus}",
                            "cuda_graph": bool(use_graph),
                            "host_images": ("float32 (divided by 255 on the host, as the reference loader)" if args.float_images
@@ -544,11 +573,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="transformer", choices=["transformer", "pointmlp"],
+                    help="transformer = BASELINE configs[1] (headline); pointmlp = configs[2] per-GPU share (4 objects)")
     ap.add_argument("--fp32", action="store_true", help="keep the backbone GEMMs in fp32 (reference precision)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--float-images", action="store_true", help="host batches carry float32 images (4x the H2D bytes)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -158,6 +158,12 @@ UP3D_API int up3d_raster_debug_state(const up3d_raster_desc *d, const void *stat
                             float *depths, float *xy, float *conic_opacity, float *rgb, int32_t *rects,
                             float *final_T, int32_t *n_contrib, up3d_stream_t stream);
 
+/* Coarse-bin decision of the forward (views of large sets with small footprints are blended from per-bin candidate
+ * lists instead of the whole view): bin_mode (n_views) int32 1 = binned, bin_total (n_views) int32 = sum over the
+ * view's visible records of the 64x64-pixel bins they touch (0 when the configuration never bins). */
+UP3D_API int up3d_raster_debug_bins(const up3d_raster_desc *d, const void *state, int32_t *bin_mode, int32_t *bin_total,
+                                    up3d_stream_t stream);
+
 /* Per-tile lists exactly as the reference's global (tile|depth) sort would produce them.
  * tile_counts (n_views, tiles) int32 is always written; when tile_lists != NULL the ids of tile t of
  * view v are written at tile_lists[view_list_start_h-style offsets]: the caller passes
@@ -403,6 +409,26 @@ UP3D_API int up3d_stem_group_stats(int n_images, int H, int W, int C, int G, con
 UP3D_API int up3d_set_pdl(int enabled);
 UP3D_API int up3d_tc_linear(int T, int N, int K, const void *A, const void *B, int b_major, const void *bias, int epilogue,
                             const void *aux_in, void *aux_out, void *out, int out_f32, int tile_n, up3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse 3-D convolution for the scene-level backbones: the arithmetic the reference takes from the un-vendored spconv
+ * package (spconv.SubMConv3d / SparseConv3d / SparseInverseConv3d in
+ * /root/reference/pointcept/models/sparse_unet/spconv_unet_v1m1_base.py:57-83,153-160,209-216,247-253 and
+ * point_transformer_v3m1_base.py:281-287).  Output-stationary implicit GEMM over a rulebook
+ * nbr (kernel_volume, n_out) int32: nbr[o][i] = input row read by kernel offset o for output row i, -1 = none.
+ *   up3d_sparse_subm_rulebook: keys_sorted (n) int64 = batch<<48 | c0<<32 | c1<<16 | c2 ascending, coords (n,4) int32
+ *     (batch, c0, c1, c2) in the same order -> nbr (k^3, n); offset o = (a*k + b)*k + c reads coord + (a,b,c) - k/2.
+ *   up3d_sparse_conv: out (n_out, c_out) fp32 = sum_o in[nbr[o][i]] (fp32, rounded to bf16) x weight[o] (c_in, c_out) bf16,
+ *     fp32 accumulation on the tensor cores; deterministic.  The input gradient is the same call with the transposed
+ *     rulebook and per-offset transposed weights.  Channels are multiples of 16 (callers zero-pad).
+ *   up3d_sparse_conv_wgrad: dweight (kernel_volume, c_in, c_out) fp32 += sum_i in[nbr[o][i]]^T dout[i] (fp32 atomics).
+ * ---------------------------------------------------------------------------------------- */
+UP3D_API int up3d_sparse_subm_rulebook(int n, int kernel_size, const int64_t *keys_sorted, const int32_t *coords,
+                                       int32_t *nbr, up3d_stream_t stream);
+UP3D_API int up3d_sparse_conv(int n_out, int c_in, int c_out, int kernel_volume, const int32_t *nbr, const float *in,
+                              const void *weight_bf16, float *out, up3d_stream_t stream);
+UP3D_API int up3d_sparse_conv_wgrad(int n_out, int c_in, int c_out, int kernel_volume, const int32_t *nbr, const float *in,
+                                    const float *dout, float *dweight, up3d_stream_t stream);
 
 #ifdef __cplusplus
 }

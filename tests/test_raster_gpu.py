@@ -372,3 +372,56 @@ def test_raster_only_headline_views_match_oracle(oracle):
     """Two views (one object) of the P = 8192 / 256x256 raster-only headline against the C oracle: bit-exact tile lists
     (2.1 M entries per view), image <= 2e-5, gradients per the stated tolerance."""
     _batch_vs_oracle(oracle, B=1, V=2, P=8192, W=256, H=256, n_oracle_views=2, check_lists=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Small-footprint regime on many tiles (the scene-level shape of BASELINE configs[3]/[4]): the blend kernels stream
+# per-bin candidate lists instead of whole views.  Lists, images and gradients must not change.
+@pytest.mark.parametrize("P,W,H,regime,expect_binned", [(30000, 512, 512, "small", True), (100000, 512, 512, "small", True),
+                                                        (20000, 320, 240, "small", True), (4096, 256, 256, "reference", False)])
+def test_binned_views_match_oracle(oracle, P, W, H, regime, expect_binned):
+    from unipre3d_b200.rasterizer import debug_forward_state, rasterize_batch
+    g = make_gaussians(P, seed=P + 1, regime=regime, sh_coeffs=4)
+    c = make_camera(az=57.0, el=12.0)
+    bg = (0.1, 0.2, 0.3)
+    sc = oracle_scene(g, c, W, H, sh_degree=1, bg=bg)
+    geo = oracle.preprocess(sc)
+    _, pl, ranges = oracle.bin_tiles(sc, geo)
+    color, fT, nc = oracle.blend_forward(sc, geo, pl, ranges)
+    t, cam = _tensors(g, c, bg, requires_grad=True)
+    out = debug_forward_state(t["means3D"].detach(), t["opacities"].detach(), t["scales"].detach(), t["rotations"].detach(),
+                              cam["viewmats"], cam["projmats"], cam["campos"], cam["bg"], set_sizes=[P], views_per_set=[1],
+                              shs=t["shs"].detach(), **_kw(c, W, H, 1))
+    assert bool(out["bin_mode"][0]) == expect_binned, (int(out["bin_mode"][0]), int(out["bin_total"][0]), int(out["n_visible"][0]))
+    counts = out["tile_counts"].cpu().numpy()[0]
+    assert np.array_equal(counts, (ranges[:, 1] - ranges[:, 0]).astype(np.int64))
+    assert np.array_equal(out["tile_lists"].cpu().numpy()[: len(pl)], pl.astype(np.int32)), "tile lists differ"
+    assert_image_close(out["color"][0].cpu().numpy(), color)
+    assert_image_close(out["final_T"][0].cpu().numpy(), fT)
+    assert (out["n_contrib"][0].cpu().numpy() != nc.astype(np.int32)).mean() <= 2e-3
+    # backward through the same (binned) path
+    dL = np.random.default_rng(P).normal(size=(3, H, W)).astype(np.float32)
+    ref = oracle.render(sc, dL)
+    img, _, _ = rasterize_batch(t["means3D"], t["opacities"], t["scales"], t["rotations"], cam["viewmats"], cam["projmats"],
+                                cam["campos"], cam["bg"], set_sizes=[P], views_per_set=[1], shs=t["shs"], **_kw(c, W, H, 1))
+    (img[0] * _dev(dL)).sum().backward()
+    for k in ["means3D", "opacities", "scales", "rotations", "shs"]:
+        assert_grad_close(t[k].grad.cpu().numpy().reshape(ref["grads"][k].shape), ref["grads"][k], k)
+
+
+def test_mixed_batch_binned_and_dense_views(oracle):
+    """One call, two sets: small splats (binned) and the reference regime (dense: every Gaussian covers every tile)."""
+    from unipre3d_b200.rasterizer import debug_forward_state
+    W = H = 256
+    sizes = [6000, 2048]
+    gs = [make_gaussians(sizes[0], seed=1, regime="small"), make_gaussians(sizes[1], seed=2, regime="reference")]
+    cams = [make_camera(az=10, el=20), make_camera(az=200, el=40)]
+    cat = {k: _dev(np.concatenate([g[k] for g in gs], 0)) for k in gs[0]}
+    vm, pm = _dev(np.stack([c["view"] for c in cams])), _dev(np.stack([c["proj"] for c in cams]))
+    cp = _dev(np.stack([c["campos"] for c in cams]))
+    out = debug_forward_state(cat["means3D"], cat["opacities"], cat["scales"], cat["rotations"], vm, pm, cp, _dev([0, 0, 0]),
+                              set_sizes=sizes, views_per_set=[1, 1], shs=cat["shs"], tile_lists=False, **_kw(cams[0], W, H, 1))
+    assert out["bin_mode"].cpu().tolist() == [1, 0]
+    for i in range(2):
+        ref = oracle.render(oracle_scene(gs[i], cams[i], W, H, sh_degree=1))
+        assert_image_close(out["color"][i].cpu().numpy(), ref["color"])

@@ -48,6 +48,7 @@ def _load() -> C.CDLL:
         "up3d_raster_backward": (i32, [D] + [vp] * 21),
         "up3d_raster_debug_state": (i32, [D] + [vp] * 11),
         "up3d_raster_debug_tile_lists": (i32, [D] + [vp] * 5),
+        "up3d_raster_debug_bins": (i32, [D] + [vp] * 4),
         "up3d_focal_l2_loss": (i32, [i64, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp]),
         "up3d_focal_l2_loss_strided": (i32, [i64, i32, i32, vp, vp, i32, i64, i64, vp, f32, f32, vp, vp, vp]),
         "up3d_raster_timing_enable": (i32, [i32]),
@@ -83,6 +84,9 @@ def _load() -> C.CDLL:
         "up3d_adamw_apply": (i32, [i32, i32] + [vp] * 10 + [f32] * 6 + [vp, vp]),
         "up3d_grad_sumsq": (i32, [i32, i32] + [vp] * 4 + [f32, vp, vp]),
         "up3d_set_pdl": (i32, [i32]),
+        "up3d_sparse_subm_rulebook": (i32, [i32, i32, vp, vp, vp, vp]),
+        "up3d_sparse_conv": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+        "up3d_sparse_conv_wgrad": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_tc_linear": (i32, [i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -96,7 +100,7 @@ lib = _load()
 EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_resident_points", "up3d_ball_query",
             "up3d_group_points", "up3d_group_points_grad", "up3d_gather_points", "up3d_gather_points_grad",
             "up3d_subsample_group", "up3d_knn", "up3d_raster_state_bytes", "up3d_raster_scratch_bytes", "up3d_raster_forward",
-            "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_focal_l2_loss",
+            "up3d_raster_backward", "up3d_raster_debug_state", "up3d_raster_debug_tile_lists", "up3d_raster_debug_bins", "up3d_focal_l2_loss",
             "up3d_focal_l2_loss_strided",
             "up3d_raster_timing_enable", "up3d_raster_timing_read", "up3d_ln_fwd", "up3d_ln_bwd", "up3d_gelu_fwd",
             "up3d_gelu_bwd", "up3d_scale_cast_colsum", "up3d_adamw_chunk_elems", "up3d_adamw_step", "up3d_adamw_apply",
@@ -105,7 +109,8 @@ EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_residen
             "up3d_bn_reduce_finalize", "up3d_gbn_stats", "up3d_gbn_apply_relu", "up3d_gbn_bwd_reduce", "up3d_gbn_bwd_apply",
             "up3d_group_max", "up3d_group_max_scatter", "up3d_group_combine", "up3d_attn_max_len", "up3d_attn_fwd",
             "up3d_attn_bwd", "up3d_splat_head_fwd", "up3d_splat_head_bwd", "up3d_fusion_project",
-            "up3d_zorder_keys", "up3d_tc_linear", "up3d_set_pdl"]
+            "up3d_zorder_keys", "up3d_tc_linear", "up3d_set_pdl", "up3d_sparse_subm_rulebook",
+            "up3d_sparse_conv", "up3d_sparse_conv_wgrad"]
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(os.path.dirname(HERE), "lib")
 LIB = os.path.join(LIB_DIR, "libunipre3d_b200.so")
-SOURCES = ["raster.cu", "pointops.cu", "loss.cu", "backbone.cu", "stem.cu", "pointnet.cu", "attention.cu", "attention_mma.cu", "head.cu", "serialize.cu", "gemm_tc.cu"]
+SOURCES = ["raster.cu", "pointops.cu", "loss.cu", "backbone.cu", "stem.cu", "pointnet.cu", "attention.cu", "attention_mma.cu", "head.cu", "serialize.cu", "gemm_tc.cu", "sparse_conv.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "up3d.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -71,8 +71,26 @@ struct State {
     uint32_t *s_rect;
     float *final_T;      // V*H*W
     int32_t *n_contrib;  // V*H*W
+    // coarse bins (BIN_TILES x BIN_TILES tiles each) for views whose Gaussians have small footprints: bin b of view v lists,
+    // in depth order, the positions k (into the view's sorted records) whose rectangle touches the bin.
+    int32_t *bin_mode;   // V: 1 = the blend kernels stream bin lists, 0 = they stream the whole view
+    int32_t *bin_total;  // V: sum over the view's records of the bins they touch
+    int32_t *bin_count;  // V * nbins
+    int32_t *bin_start;  // V * nbins: offset of the bin's list inside the view's region of bin_list
+    int32_t *bin_list;   // BIN_CAP * R: the view's region starts at BIN_CAP * view_rec_start[v]
+    int nbins_x, nbins_y;
     size_t total;
 };
+
+constexpr int BIN_TILES = 4;          // a bin is 4 x 4 tiles = 64 x 64 pixels
+constexpr int BIN_CAP = 8;            // a view is binned when its records touch <= BIN_CAP bins on average
+constexpr int BIN_MIN_SET = 1024;     // smaller sets stream all their records (the object-level transformer regime)
+constexpr int BIN_MIN_TILES = 64;
+
+static inline bool bins_enabled(const up3d_raster_desc *d) {
+    const int gx = (d->width + UP3D_TILE - 1) / UP3D_TILE, gy = (d->height + UP3D_TILE - 1) / UP3D_TILE;
+    return d->max_set_size >= BIN_MIN_SET && gx * gy >= BIN_MIN_TILES;
+}
 
 static State carve_state(const up3d_raster_desc *d, void *base) {
     State s;
@@ -98,6 +116,18 @@ static State carve_state(const up3d_raster_desc *d, void *base) {
     CARVE(s_rect, uint32_t, R)
     CARVE(final_T, float, V * HW)
     CARVE(n_contrib, int32_t, V * HW)
+    {
+        const int gx = (d->width + UP3D_TILE - 1) / UP3D_TILE, gy = (d->height + UP3D_TILE - 1) / UP3D_TILE;
+        s.nbins_x = (gx + BIN_TILES - 1) / BIN_TILES;
+        s.nbins_y = (gy + BIN_TILES - 1) / BIN_TILES;
+        const size_t nb = (size_t)s.nbins_x * s.nbins_y;
+        const bool on = bins_enabled(d);
+        CARVE(bin_mode, int32_t, V)
+        CARVE(bin_total, int32_t, V)
+        CARVE(bin_count, int32_t, on ? V * nb : 1)
+        CARVE(bin_start, int32_t, on ? V * nb : 1)
+        CARVE(bin_list, int32_t, on ? (size_t)BIN_CAP * R : 1)
+    }
 #undef CARVE
     s.total = off;
     return s;
@@ -475,12 +505,108 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) depth_sort_kernel(const SortA
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. blend forward (A.6)
+// 2b. coarse bins (small-footprint views only)
+//
+// In the reference's object regime every Gaussian covers every tile and a tile's list IS the view's depth order, so the
+// blend kernels stream the view's records.  With 10^5 small splats on 1024 tiles that would stage tiles * P records per
+// view; instead each 4x4-tile bin gets the depth-ordered list of record positions touching it (order-preserving ballot
+// compaction of the already sorted records, so per-tile lists stay bit-exact), and a tile streams only its bin.
+// Three small kernels: per-view total of touched bins -> decision; per-bin counts; per-bin ordered fill.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool rect_covers(uint32_t rect, int tx, int ty) {
     const int minx = rect & 0xFF, miny = (rect >> 8) & 0xFF, maxx = (rect >> 16) & 0xFF, maxy = rect >> 24;
     return tx >= minx && tx < maxx && ty >= miny && ty < maxy;
 }
+// bin range [bx0, bx1] x [by0, by1] touched by a (non-empty) tile rectangle
+__device__ __forceinline__ void rect_bins(uint32_t rect, int &bx0, int &by0, int &bx1, int &by1) {
+    const int minx = rect & 0xFF, miny = (rect >> 8) & 0xFF, maxx = (rect >> 16) & 0xFF, maxy = rect >> 24;
+    bx0 = minx / BIN_TILES; by0 = miny / BIN_TILES; bx1 = (maxx - 1) / BIN_TILES; by1 = (maxy - 1) / BIN_TILES;
+}
+__device__ __forceinline__ bool rect_touches_bin(uint32_t rect, int bx, int by) {
+    int bx0, by0, bx1, by1;
+    rect_bins(rect, bx0, by0, bx1, by1);
+    return bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1;
+}
+
+struct BinArgs {
+    const int32_t *view_rec_start;
+    State st;
+};
+
+// grid (ceil(max_set/256), V): bin_total[v] = sum over sorted records of the number of bins they touch
+__global__ void __launch_bounds__(256) bin_total_kernel(const BinArgs a) {
+    const int v = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+    const int rec0 = a.view_rec_start[v], n = a.st.n_vis[v];
+    int nb = 0;
+    if (k < n) {
+        int bx0, by0, bx1, by1;
+        rect_bins(a.st.s_rect[rec0 + k], bx0, by0, bx1, by1);
+        nb = (bx1 - bx0 + 1) * (by1 - by0 + 1);
+    }
+    nb = __reduce_add_sync(0xffffffffu, nb);
+    if ((threadIdx.x & 31) == 0 && nb) atomicAdd(&a.st.bin_total[v], nb);
+}
+
+// grid (ceil(max_set/256), V): decides the mode, then (binned views only) per-bin counts
+__global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
+    const int v = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+    const int rec0 = a.view_rec_start[v], n = a.st.n_vis[v];
+    const int cap = BIN_CAP * (a.view_rec_start[v + 1] - rec0);
+    const bool binned = a.st.bin_total[v] <= cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.st.bin_mode[v] = binned ? 1 : 0;
+    if (!binned || k >= n) return;
+    int bx0, by0, bx1, by1;
+    rect_bins(a.st.s_rect[rec0 + k], bx0, by0, bx1, by1);
+    int32_t *cnt = a.st.bin_count + (size_t)v * a.st.nbins_x * a.st.nbins_y;
+    for (int by = by0; by <= by1; ++by)
+        for (int bx = bx0; bx <= bx1; ++bx) atomicAdd(&cnt[by * a.st.nbins_x + bx], 1);
+}
+
+// grid (nbins, V): ordered fill of bin b's list (positions k, ascending = depth order)
+__global__ void __launch_bounds__(256) bin_fill_kernel(const BinArgs a) {
+    __shared__ int warp_cnt[8];
+    __shared__ int s_start;
+    const int v = blockIdx.y, b = blockIdx.x;
+    if (!a.st.bin_mode[v]) return;
+    const int nb = a.st.nbins_x * a.st.nbins_y;
+    const int32_t *cnt = a.st.bin_count + (size_t)v * nb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // exclusive prefix of the counts of bins < b
+    int part = 0;
+    for (int i = tid; i < b; i += 256) part += cnt[i];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) warp_cnt[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_cnt[w];
+        s_start = t;
+        a.st.bin_start[(size_t)v * nb + b] = t;
+    }
+    __syncthreads();
+    if (cnt[b] == 0) return;
+    const int rec0 = a.view_rec_start[v], n = a.st.n_vis[v];
+    int32_t *dst = a.st.bin_list + (size_t)BIN_CAP * rec0 + s_start;
+    const int bx = b % a.st.nbins_x, by = b / a.st.nbins_x;
+    int run = 0;
+    for (int base = 0; base < n; base += 256) {
+        const int k = base + tid;
+        const bool hit = (k < n) && rect_touches_bin(a.st.s_rect[rec0 + k], bx, by);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        __syncthreads();
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { off += (w < warp) ? warp_cnt[w] : 0; total += warp_cnt[w]; }
+        if (hit) dst[run + off + __popc(bal & lanemask_lt())] = k;
+        run += total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. blend forward (A.6)
+// ------------------------------------------------------------------------------------------------
 
 // power = -0.5f * (co.x*dx*dx + co.z*dy*dy) - co.y*dx*dy with the operation order nvcc gives the upstream
 // expression (so the power > 0 / alpha < 1/255 skip decisions do not depend on this compiler's contraction
@@ -553,6 +679,38 @@ __device__ __forceinline__ void stage_fill_plain(StageBuf &sb, const State &st, 
     }
 }
 
+// binned views: chunk [base, base + 256) of a bin's list of record positions -> gathered into the staging buffer
+template <bool WITH_ID>
+__device__ __forceinline__ void stage_fill_indexed(StageBuf &sb, const State &st, int rec0, const int32_t *list, int n, int base) {
+    const int tid = threadIdx.x, i = base + tid;
+    if (i < n) {
+        const int k = rec0 + list[i];
+        sb.xy[tid] = st.s_xy[k];
+        sb.co[tid] = st.s_co[k];
+        sb.rgb[tid] = st.s_rgb[k];
+        sb.rect[tid] = st.s_rect[k];
+        if (WITH_ID) sb.id[tid] = st.s_id[k];
+    }
+}
+
+// The candidate records of tile (tx, ty) of view v: the whole view (list == nullptr, n = n_vis) or its bin's list.
+struct Candidates {
+    const int32_t *list;
+    int n;
+};
+__device__ __forceinline__ Candidates tile_candidates(const State &st, const int32_t *view_rec_start, int v, int tx, int ty) {
+    Candidates c;
+    if (st.bin_mode[v]) {
+        const int nb = st.nbins_x * st.nbins_y, b = (ty / BIN_TILES) * st.nbins_x + tx / BIN_TILES;
+        c.list = st.bin_list + (size_t)BIN_CAP * view_rec_start[v] + st.bin_start[(size_t)v * nb + b];
+        c.n = st.bin_count[(size_t)v * nb + b];
+    } else {
+        c.list = nullptr;
+        c.n = st.n_vis[v];
+    }
+    return c;
+}
+
 // In-place ordered compaction of a staged chunk to the records covering tile (tx, ty).  Returns the number kept.
 // All 256 threads call; the staged data must be visible (mbarrier wait / __syncthreads) to all of them.
 template <bool WITH_ID>
@@ -588,6 +746,9 @@ struct BlendArgs {
     State st;
 };
 
+// BINS: compiled-in support for binned views (host enables it for large sets on many tiles only; the object-level
+// configurations run the leaner BINS = false instantiation: 32 vs 48 registers -> 8 vs 5 resident CTAs per SM).
+template <bool BINS>
 __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_forward_kernel(const BlendArgs a) {
     __shared__ StageBuf stage[2];
     __shared__ __align__(8) uint64_t bar[2];
@@ -597,9 +758,12 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_forward_kernel(const Blen
     const int px = tx * UP3D_TILE + (tid & 15), py = ty * UP3D_TILE + (tid >> 4);
     const bool inside = px < a.W && py < a.H;
     const int rec0 = a.view_rec_start[v];
-    const int n = a.st.n_vis[v];
+    Candidates cand{nullptr, 0};
+    if (BINS) cand = tile_candidates(a.st, a.view_rec_start, v, tx, ty);
+    else cand.n = a.st.n_vis[v];
+    const int n = cand.n;
     const float pfx = (float)px, pfy = (float)py;
-    const bool tma = (rec0 & 3) == 0;          // every slice of the view's records starts 16-byte aligned
+    const bool tma = cand.list == nullptr && (rec0 & 3) == 0;   // every slice of the view's records starts 16-byte aligned
     const int nchunks = (n + UP3D_TILE_PIX - 1) / UP3D_TILE_PIX;
     if (tma && tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
     __syncthreads();
@@ -621,7 +785,8 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_forward_kernel(const Blen
             }
             mbar_wait(&bar[c & 1], (uint32_t)((c >> 1) & 1));
         } else {
-            stage_fill_plain<false>(sb, a.st, rec0, n, c * UP3D_TILE_PIX);
+            if (BINS && cand.list) stage_fill_indexed<false>(sb, a.st, rec0, cand.list, n, c * UP3D_TILE_PIX);
+            else stage_fill_plain<false>(sb, a.st, rec0, n, c * UP3D_TILE_PIX);
             __syncthreads();
         }
         const int cnt = stage_compact<false>(sb, warp_cnt, n, c * UP3D_TILE_PIX, tx, ty);
@@ -691,6 +856,7 @@ struct BwdSmem {
     int red[8];
 };
 
+template <bool BINS>
 __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const BlendBwdArgs a) {
     extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(bwd_smem_raw);
@@ -700,13 +866,16 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
     const int px = tx * UP3D_TILE + (tid & 15), py = ty * UP3D_TILE + (tid >> 4);
     const bool inside = px < a.W && py < a.H;
     const int rec0 = a.view_rec_start[v];
-    const int n = a.st.n_vis[v];
+    Candidates cand{nullptr, 0};
+    if (BINS) cand = tile_candidates(a.st, a.view_rec_start, v, tx, ty);
+    else cand.n = a.st.n_vis[v];
+    const int n = cand.n;
     const size_t HW = (size_t)a.W * a.H, pix = (size_t)py * a.W + px;
     const float pfx = (float)px, pfy = (float)py;
 
     const float T_final = inside ? a.st.final_T[v * HW + pix] : 0.f;
     const int last_contributor = inside ? a.st.n_contrib[v * HW + pix] : 0;
-    const bool tma = (rec0 & 3) == 0;
+    const bool tma = cand.list == nullptr && (rec0 & 3) == 0;
     if (tma && tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
     int m = __reduce_max_sync(0xffffffffu, last_contributor);
     if (lane == 0) sm.red[warp] = m;
@@ -728,7 +897,7 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
     int c_last = 0, cum = 0;
     for (int base = 0; base < n; base += UP3D_TILE_PIX) {
         const int k = base + tid;
-        const bool hit = (k < n) && rect_covers(a.st.s_rect[rec0 + k], tx, ty);
+        const bool hit = (k < n) && rect_covers(a.st.s_rect[rec0 + ((BINS && cand.list) ? cand.list[k] : k)], tx, ty);
         cum += __syncthreads_count(hit);
         c_last = base / UP3D_TILE_PIX;
         if (cum >= Lmax) break;
@@ -752,7 +921,8 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
             mbar_wait(&sm.bar, loads & 1u);
             ++loads;
         } else {
-            stage_fill_plain<true>(ch, a.st, rec0, n, c * UP3D_TILE_PIX);
+            if (BINS && cand.list) stage_fill_indexed<true>(ch, a.st, rec0, cand.list, n, c * UP3D_TILE_PIX);
+            else stage_fill_plain<true>(ch, a.st, rec0, n, c * UP3D_TILE_PIX);
             __syncthreads();
         }
         const int cnt = stage_compact<true>(ch, sm.warp_cnt, n, c * UP3D_TILE_PIX, tx, ty);
@@ -1134,7 +1304,7 @@ static int ensure_dyn_smem(const void *fn, std::atomic<size_t> &configured, size
     while (cur < bytes && !configured.compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
     return 0;
 }
-static std::atomic<size_t> g_sort_smem{0}, g_bwd_smem{0};
+static std::atomic<size_t> g_sort_smem{0}, g_bwd_smem{0}, g_bwd_smem_bins{0};
 
 static ViewConst make_view_const(const up3d_raster_desc *d) {
     ViewConst vc;
@@ -1201,10 +1371,23 @@ int up3d_raster_forward(const up3d_raster_desc *d, const float *means3D, const f
         depth_sort_kernel<<<V, SORT_THREADS, smem, stream>>>(sa);
         UP3D_LAUNCH_OK("depth_sort_kernel");
     }
+    // bin decision + lists (large, many-tile problems only; otherwise every view streams its records)
+    UP3D_CUDA_OK(cudaMemsetAsync(st.bin_mode, 0, (size_t)((char *)st.bin_count - (char *)st.bin_mode), stream));   // mode + total
+    if (bins_enabled(d)) {
+        const size_t nb = (size_t)st.nbins_x * st.nbins_y;
+        UP3D_CUDA_OK(cudaMemsetAsync(st.bin_count, 0, sizeof(int32_t) * V * nb, stream));
+        BinArgs ba{d->view_rec_start, st};
+        const dim3 grid_r(div_up(d->max_set_size, 256), V);
+        bin_total_kernel<<<grid_r, 256, 0, stream>>>(ba);
+        bin_count_kernel<<<grid_r, 256, 0, stream>>>(ba);
+        bin_fill_kernel<<<dim3((unsigned)nb, V), 256, 0, stream>>>(ba);
+        UP3D_LAUNCH_OK("bin kernels");
+    }
     tick(2, stream);
     {
         BlendArgs ba{d->width, d->height, d->view_rec_start, bg, out_color, invdepth, st};
-        blend_forward_kernel<<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, 0, stream>>>(ba);
+        if (bins_enabled(d)) blend_forward_kernel<true><<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, 0, stream>>>(ba);
+        else blend_forward_kernel<false><<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, 0, stream>>>(ba);
         UP3D_LAUNCH_OK("blend_forward_kernel");
     }
     tick(3, stream);
@@ -1230,13 +1413,16 @@ int up3d_raster_backward(const up3d_raster_desc *d, const float *means3D, const 
     Scratch sc = carve_scratch(d, scratch);
     const ViewConst vc = make_view_const(d);
     const int V = d->n_views;
-    if (ensure_dyn_smem((const void *)blend_backward_kernel, g_bwd_smem, sizeof(BwdSmem))) return 1;
+    const bool bins = bins_enabled(d);
+    if (ensure_dyn_smem(bins ? (const void *)blend_backward_kernel<true> : (const void *)blend_backward_kernel<false>,
+                        bins ? g_bwd_smem_bins : g_bwd_smem, sizeof(BwdSmem))) return 1;
     tick(4, stream);
     UP3D_CUDA_OK(cudaMemsetAsync(sc.gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)d->n_records, stream));
     tick(5, stream);
     if (V > 0) {
         BlendBwdArgs ba{d->width, d->height, d->view_rec_start, bg, dL_dcolor, sc.gacc, st};
-        blend_backward_kernel<<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, sizeof(BwdSmem), stream>>>(ba);
+        if (bins) blend_backward_kernel<true><<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, sizeof(BwdSmem), stream>>>(ba);
+        else blend_backward_kernel<false><<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, sizeof(BwdSmem), stream>>>(ba);
         UP3D_LAUNCH_OK("blend_backward_kernel");
     }
     tick(6, stream);
@@ -1296,6 +1482,17 @@ int up3d_raster_debug_state(const up3d_raster_desc *d, const void *state, int32_
         debug_unpack_kernel<<<div_up(d->n_records, 256), 256, 0, stream>>>(d->n_records, st, depths, xy, conic_opacity, rgb, rects);
         UP3D_LAUNCH_OK("debug_unpack_kernel");
     }
+    return 0;
+}
+
+int up3d_raster_debug_bins(const up3d_raster_desc *d, const void *state, int32_t *bin_mode, int32_t *bin_total,
+                           up3d_stream_t stream_) {
+    if (validate_desc(d)) return 1;
+    UP3D_CHECK_ARG(state != nullptr, "up3d_raster_debug_bins: null state");
+    State st = carve_state(d, const_cast<void *>(state));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (bin_mode) UP3D_CUDA_OK(cudaMemcpyAsync(bin_mode, st.bin_mode, 4 * (size_t)d->n_views, cudaMemcpyDeviceToDevice, stream));
+    if (bin_total) UP3D_CUDA_OK(cudaMemcpyAsync(bin_total, st.bin_total, 4 * (size_t)d->n_views, cudaMemcpyDeviceToDevice, stream));
     return 0;
 }
 

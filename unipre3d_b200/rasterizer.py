@@ -195,6 +195,8 @@ def debug_forward_state(means3D, opacities, scales, rotations, viewmats, projmat
                                                ptr(out["depths"]), ptr(out["xy"]), ptr(out["conic_opacity"]),
                                                ptr(out["rgb"]), ptr(out["rects"]), ptr(out["final_T"]),
                                                ptr(out["n_contrib"]), stream_ptr()), launches=1)
+        out.update(bin_mode=torch.zeros(V, **i32), bin_total=torch.zeros(V, **i32))
+        check(_lib.lib.up3d_raster_debug_bins(C.byref(d), ptr(state), ptr(out["bin_mode"]), ptr(out["bin_total"]), stream_ptr()))
         if tile_lists:
             tiles = ((W + 15) // 16) * ((H + 15) // 16)
             counts = torch.zeros(V * tiles, **i32)
