@@ -91,12 +91,18 @@ def _sync_worker(rank, world, port, out_dir, overlap):
         early = [torch.nn.Parameter(torch.zeros(s)) for s in ((7, 5), (11,), (3, 4, 2))]
         rest = [torch.nn.Parameter(torch.zeros(s)) for s in ((6,), (2, 9))]
         params = [rest[0]] + early + [rest[1]]                  # optimizer order differs from the flat-buffer order
-        gs = GradSync(params, early, "cpu", overlap=overlap)
+        chunks = overlap == "chunks"
+        gs = GradSync(params, early, "cpu", overlap=bool(overlap))
         for step in range(2):                                   # two steps: buffers and handles are reused
             g = torch.Generator().manual_seed(100 * step + rank)
             eg = [torch.randn(p.shape, generator=g) for p in early]
             rg = [torch.randn(p.shape, generator=g) for p in rest]
-            got = gs.early_hook(eg)                             # fires in the middle of the "backward"
+            if chunks:                                          # chunk-wise, last parameters first (backward order)
+                gs.early_chunk_hook(2, eg[2:])
+                gs.early_chunk_hook(0, eg[:2])
+                got = eg
+            else:
+                got = gs.early_hook(eg)                         # fires in the middle of the "backward"
             assert all(a is b for a, b in zip(got, eg))
             for p, t in zip(early, got):
                 p.grad = t
@@ -105,7 +111,7 @@ def _sync_worker(rank, world, port, out_dir, overlap):
             gs.finish()
             assert all(p.grad.data_ptr() >= gs.flat.data_ptr() for p in params)     # views of the flat buffer
         if rank == 0:
-            torch.save([p.grad.clone() for p in early + rest], os.path.join(out_dir, f"sync_{int(overlap)}.pt"))
+            torch.save([p.grad.clone() for p in early + rest], os.path.join(out_dir, f"sync_{overlap}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -114,10 +120,10 @@ def test_grad_sync_overlapped_all_reduce_sums_over_ranks():
     """grad_sync.GradSync (the N > 1 gradient exchange of the GPU trainer) over two gloo ranks: the early (in-backward)
     all-reduce on its own communicator + the tail all-reduce give the SUM over ranks, with and without the overlap."""
     world, shapes_e, shapes_r = 2, ((7, 5), (11,), (3, 4, 2)), ((6,), (2, 9))
-    for overlap in (True, False):
+    for overlap in (True, False, "chunks"):
         with tempfile.TemporaryDirectory() as td:
             mp.spawn(_sync_worker, args=(world, _free_port(), td, overlap), nprocs=world, join=True)
-            got = torch.load(os.path.join(td, f"sync_{int(overlap)}.pt"))
+            got = torch.load(os.path.join(td, f"sync_{overlap}.pt"))
         want = None
         for rank in range(world):
             g = torch.Generator().manual_seed(100 * 1 + rank)   # the second step's gradients

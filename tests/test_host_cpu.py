@@ -286,3 +286,24 @@ def test_checkpoint_round_trip_keeps_reference_keys(tmp_path):
     c = ModelManager(cfg, torch.device("cpu"))
     assert c.load_checkpoint(str(tmp_path / "ref_style.pth")) == {"iteration": 7, "best_PSNR": 1.0}
     assert c._sched_step == 7 and (c.ema is None or (c.ema.step == 7 and c.ema.initted))
+
+
+def test_packed_batch_is_one_buffer_with_aligned_views():
+    """trainer.PackedBatch: the flat pinned staging form of a batch dict (one H2D + one D2D per step)."""
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.config import compose
+    from unipre3d_b200.trainer import PackedBatch
+    cfg = compose(overrides=["data.training_resolution=32", "opt.batch_size=2"])
+    b = synthetic.make_batch(cfg, 2, 128, seed=0, image_dtype="uint8")
+    p = PackedBatch(b, pin=False)
+    assert p.flat.dtype == torch.uint8 and p.flat.numel() == p.nbytes
+    assert all(off % 256 == 0 for _, off, _, _, _ in p.layout)
+    assert p.nbytes >= synthetic.batch_nbytes(b) and p.nbytes < synthetic.batch_nbytes(b) + 256 * len(p.layout)
+    assert torch.equal(p.data["gt_images"], b["gt_images"]) and p.data["gt_images"].dtype == torch.uint8
+    assert torch.equal(p.data["point_cloud"]["pos"], b["point_cloud"]["pos"])
+    base = p.flat.data_ptr()
+    assert all(base <= t.data_ptr() < base + p.nbytes for t in (p.data["gt_images"], p.data["camera_centers"]))
+    mirror = p.views(p.flat.clone())                       # what the trainer builds on the device
+    for k in ("world_view_transforms", "full_proj_transforms", "view_to_world_transforms", "camera_centers"):
+        assert torch.equal(mirror[k], b[k])
+    assert PackedBatch(b, pin=False).signature() == p.signature()

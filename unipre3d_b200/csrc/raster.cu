@@ -25,6 +25,7 @@
 //             5. geometry_backward_kernel : per Gaussian, loops over the views of its set in a fixed
 //                order and writes dL/d{xyz, scale, rot, opacity, SH}.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -843,9 +844,11 @@ struct BlendBwdArgs {
 // BWD_EB entries, back to front) only produces u and w into shared memory; phase 2 (16 threads per entry) forms the
 // nine moment sums over the pixels with 4 shuffle levels, and one lane per entry issues the global atomics.  This
 // replaces 45 shuffles + 9 shared atomics per (warp, entry) of the straightforward scheme.
-constexpr int BWD_EB = 16;            // entries per sub-batch
+// Sub-batch size BWD_EB: 16 entries (16 threads per entry in phase 2, 35 KB of u / w staging -> 4 CTAs per SM) or 8
+// entries (32 threads per entry, 17 KB -> 6 CTAs per SM); selected at run time (UP3D_BWD_EB, default below).
 constexpr int BWD_ROW = 256 + 16;     // padded row of the u / w staging arrays (conflict-free phase-2 reads)
 
+template <int BWD_EB>
 struct BwdSmem {
     StageBuf ch;                       // staged + in-place compacted chunk (single buffer: see kernel comment)
     uint64_t bar;
@@ -856,10 +859,12 @@ struct BwdSmem {
     int red[8];
 };
 
-template <bool BINS>
-__global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const BlendBwdArgs a) {
+template <bool BINS, int BWD_EB>
+__global__ void __launch_bounds__(UP3D_TILE_PIX, BWD_EB == 8 ? 5 : 4) blend_backward_kernel(const BlendBwdArgs a) {
     extern __shared__ __align__(16) unsigned char bwd_smem_raw[];
-    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(bwd_smem_raw);
+    BwdSmem<BWD_EB> &sm = *reinterpret_cast<BwdSmem<BWD_EB> *>(bwd_smem_raw);
+    constexpr int TPE = UP3D_TILE_PIX / BWD_EB;       // phase-2 threads per entry (16 or 32)
+    constexpr int PPT = UP3D_TILE_PIX / TPE;          // pixels per phase-2 thread
     StageBuf &ch = sm.ch;
     const int v = blockIdx.z, tx = blockIdx.x, ty = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -908,8 +913,8 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;     // accum_rec
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;        // last_color
     float last_alpha = 0.f;
-    // phase-2 role of this thread: entry slot e2 of the sub-batch, 16 pixels {part + 16 i}
-    const int e2 = tid >> 4, part = tid & 15;
+    // phase-2 role of this thread: entry slot e2 of the sub-batch, PPT pixels {part + TPE i}
+    const int e2 = tid / TPE, part = tid % TPE;
 
     // Chunks are visited back to front.  In the reference's regime the first Lmax entries live in chunk 0, so a second
     // staging buffer would only cost occupancy (4 -> 3 CTAs/SM); one buffer, refilled by TMA after the barrier that
@@ -969,12 +974,13 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
                 float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, R0 = 0.f, R1 = 0.f, R2 = 0.f;
                 if (j >= 0) {
                     const float2 xy = ch.xy[j];
-                    const float bx = xy.x - (float)(tx * UP3D_TILE + part), by0 = xy.y - (float)(ty * UP3D_TILE);
+                    const float bx = xy.x - (float)(tx * UP3D_TILE + (part & 15));
+                    const float by0 = xy.y - (float)(ty * UP3D_TILE + (part >> 4));
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int p = part + 16 * i;         // pixel (column = part, row = i)
+                    for (int i = 0; i < PPT; ++i) {
+                        const int p = part + TPE * i;        // pixel (column = part & 15, row = (part >> 4) + (TPE / 16) i)
                         const float u = sm.u[e2][p], wv = sm.w[e2][p];
-                        const float dx = bx, dy = by0 - (float)i;
+                        const float dx = bx, dy = by0 - (float)((TPE / 16) * i);
                         const float ux = u * dx, uy = u * dy;
                         S0 += u; Sx += ux; Sy += uy;
                         Sxx = fmaf(ux, dx, Sxx); Sxy = fmaf(ux, dy, Sxy); Syy = fmaf(uy, dy, Syy);
@@ -982,7 +988,7 @@ __global__ void __launch_bounds__(UP3D_TILE_PIX) blend_backward_kernel(const Ble
                     }
                 }
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {
+                for (int o = TPE / 2; o > 0; o >>= 1) {
                     S0 += __shfl_xor_sync(0xffffffffu, S0, o); Sx += __shfl_xor_sync(0xffffffffu, Sx, o);
                     Sy += __shfl_xor_sync(0xffffffffu, Sy, o); Sxx += __shfl_xor_sync(0xffffffffu, Sxx, o);
                     Sxy += __shfl_xor_sync(0xffffffffu, Sxy, o); Syy += __shfl_xor_sync(0xffffffffu, Syy, o);
@@ -1304,7 +1310,8 @@ static int ensure_dyn_smem(const void *fn, std::atomic<size_t> &configured, size
     while (cur < bytes && !configured.compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
     return 0;
 }
-static std::atomic<size_t> g_sort_smem{0}, g_bwd_smem{0}, g_bwd_smem_bins{0};
+static std::atomic<size_t> g_sort_smem{0}, g_bwd_smem[4];
+constexpr int BWD_EB_DEFAULT = 16;
 
 static ViewConst make_view_const(const up3d_raster_desc *d) {
     ViewConst vc;
@@ -1414,15 +1421,24 @@ int up3d_raster_backward(const up3d_raster_desc *d, const float *means3D, const 
     const ViewConst vc = make_view_const(d);
     const int V = d->n_views;
     const bool bins = bins_enabled(d);
-    if (ensure_dyn_smem(bins ? (const void *)blend_backward_kernel<true> : (const void *)blend_backward_kernel<false>,
-                        bins ? g_bwd_smem_bins : g_bwd_smem, sizeof(BwdSmem))) return 1;
+    static const int eb = [] { const char *e = getenv("UP3D_BWD_EB"); return (e && atoi(e) == 16) ? 16 : (e && atoi(e) == 8) ? 8 : BWD_EB_DEFAULT; }();
+    const int variant = (bins ? 2 : 0) + (eb == 8 ? 1 : 0);
+    const void *bwd_fn[4] = {(const void *)blend_backward_kernel<false, 16>, (const void *)blend_backward_kernel<false, 8>,
+                             (const void *)blend_backward_kernel<true, 16>, (const void *)blend_backward_kernel<true, 8>};
+    const size_t bwd_smem = eb == 8 ? sizeof(BwdSmem<8>) : sizeof(BwdSmem<16>);
+    if (ensure_dyn_smem(bwd_fn[variant], g_bwd_smem[variant], bwd_smem)) return 1;
     tick(4, stream);
     UP3D_CUDA_OK(cudaMemsetAsync(sc.gacc, 0, sizeof(float) * GACC_STRIDE * (size_t)d->n_records, stream));
     tick(5, stream);
     if (V > 0) {
         BlendBwdArgs ba{d->width, d->height, d->view_rec_start, bg, dL_dcolor, sc.gacc, st};
-        if (bins) blend_backward_kernel<true><<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, sizeof(BwdSmem), stream>>>(ba);
-        else blend_backward_kernel<false><<<dim3(vc.gx, vc.gy, V), UP3D_TILE_PIX, sizeof(BwdSmem), stream>>>(ba);
+        const dim3 grid(vc.gx, vc.gy, V);
+        switch (variant) {
+            case 0: blend_backward_kernel<false, 16><<<grid, UP3D_TILE_PIX, bwd_smem, stream>>>(ba); break;
+            case 1: blend_backward_kernel<false, 8><<<grid, UP3D_TILE_PIX, bwd_smem, stream>>>(ba); break;
+            case 2: blend_backward_kernel<true, 16><<<grid, UP3D_TILE_PIX, bwd_smem, stream>>>(ba); break;
+            default: blend_backward_kernel<true, 8><<<grid, UP3D_TILE_PIX, bwd_smem, stream>>>(ba); break;
+        }
         UP3D_LAUNCH_OK("blend_backward_kernel");
     }
     tick(6, stream);

@@ -133,10 +133,11 @@ conv_kernel(int n_out, int Cin, int Cout, int KV, const int *__restrict__ nbr, c
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
-// dW[o] (Cin x Cout) += sum_i in[nbr[o][i]]^T dout[i].  grid (voxel chunks, KV, (Cin/CT) * (Cout/CT)), CT = 64 or the
-// channel count when smaller; one CTA accumulates a CT x CT tile of dW[o] over its chunk of `rows_per_cta` output rows in
+// dW[o] (Cin x Cout) += sum_i in[nbr[o][i]]^T dout[i].  grid (voxel chunks, KV, (Cin/CTi) * (Cout/CTo)), CT = 64, 32 or 16
+// (the largest that divides the channel count); one CTA accumulates a CT x CT tile of dW[o] over its chunk of `rows_per_cta` output rows in
 // registers and adds it once with fp32 atomics.
 constexpr int WG_CT = 64;
+__host__ __device__ inline int wg_tile(int c) { return c % 64 == 0 ? 64 : c % 32 == 0 ? 32 : 16; }   // e.g. 96 = 3 x 32
 __global__ void __launch_bounds__(THREADS)
 wgrad_kernel(int n_out, int Cin, int Cout, int rows_per_cta, const int *__restrict__ nbr, const float *__restrict__ in,
              const float *__restrict__ dout, float *__restrict__ dw) {
@@ -145,7 +146,7 @@ wgrad_kernel(int n_out, int Cin, int Cout, int rows_per_cta, const int *__restri
     __shared__ int s_idx[ROWS];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int o = blockIdx.y;
-    const int ci_t = min(Cin, WG_CT), co_t = min(Cout, WG_CT);
+    const int ci_t = wg_tile(Cin), co_t = wg_tile(Cout);
     const int tiles_co = Cout / co_t;
     const int ci0 = (blockIdx.z / tiles_co) * ci_t, co0 = (blockIdx.z % tiles_co) * co_t;
     const int nfr = co_t / 16;                                     // accumulator fragments per warp (<= 4)
@@ -267,9 +268,7 @@ extern "C" int up3d_sparse_conv_wgrad(int n_out, int c_in, int c_out, int kernel
                                       const float *dout, float *dweight, up3d_stream_t stream) {
     UP3D_CHECK_ARG(n_out >= 0 && c_in > 0 && c_out > 0 && kernel_volume > 0, "up3d_sparse_conv_wgrad: bad sizes");
     UP3D_CHECK_ARG(c_in % 16 == 0 && c_out % 16 == 0, "up3d_sparse_conv_wgrad: channel counts must be multiples of 16");
-    const int ci_t = c_in < sp::WG_CT ? c_in : sp::WG_CT, co_t = c_out < sp::WG_CT ? c_out : sp::WG_CT;
-    UP3D_CHECK_ARG(c_in % ci_t == 0 && c_out % co_t == 0 && ci_t % 16 == 0 && co_t % 16 == 0,
-                   "up3d_sparse_conv_wgrad: channels above 64 must be multiples of 64 (got %d -> %d)", c_in, c_out);
+    const int ci_t = sp::wg_tile(c_in), co_t = sp::wg_tile(c_out);
     if (n_out == 0) return 0;
     UP3D_CHECK_ARG(nbr && in && dout && dweight, "up3d_sparse_conv_wgrad: NULL pointer");
     // enough voxel chunks to fill the machine, at least 4 sub-tiles each

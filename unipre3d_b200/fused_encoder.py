@@ -149,6 +149,12 @@ _SIDE_STREAMS = {}
 # its parameter gradients (order = run_encoder_stack's parameter order); returns the tensors autograd should see.  The
 # trainer uses it to start the all-reduce of these ~97 % of all gradient bytes while the rest of the backward still runs.
 GRAD_READY_HOOK = None
+# Chunked variant (preferred when set): called from INSIDE the stack's backward every GRAD_CHUNK_BLOCKS blocks with
+# (first_block, gradients of blocks [first_block, first_block + n) in stack_parameters order), as soon as those blocks'
+# weight gradients exist -- the all-reduce of a chunk then overlaps the backward of the blocks in front of it instead of
+# starting when the whole stack is done.
+GRAD_CHUNK_HOOK = None
+GRAD_CHUNK_BLOCKS = 4
 
 
 class SideStream:
@@ -271,6 +277,12 @@ class EncoderStackFn(torch.autograd.Function):
             e = lambda n: torch.empty((depth, T, n), dtype=act, device=dev)
             DD, DPRE, DA, DQKV = e(C), e(Hd), e(C), e(3 * C)
             dd = scale_cast_colsum(g, s2_last, L, act, sm(depth - 1, 5), out=DD[depth - 1])
+            chunked = GRAD_CHUNK_HOOK is not None and depth % GRAD_CHUNK_BLOCKS == 0
+            wg = {}                                 # block index -> (gWqkv, gWproj, gW1, gW2) when produced chunk-wise
+
+            def block_grads(i, gWqkv_i, gWproj_i, gW1_i, gW2_i):
+                return [sm(i, 0), sm(i, 1), gWqkv_i, gWproj_i, sm(i, 2), sm(i, 3), sm(i, 4), gW1_i, sm(i, 6, Hd), gW2_i, sm(i, 5)]
+
             for i in range(depth - 1, -1, -1):
                 xs, mu1, rs1, x2, mu2, rs2, pre, qkv, lse = sv[SAVED_PER_BLOCK * i:SAVED_PER_BLOCK * (i + 1)]
                 n1w, _, _, _, _, n2w, _, _, _, _, _ = params[i * PARAMS_PER_BLOCK:(i + 1) * PARAMS_PER_BLOCK]
@@ -297,20 +309,30 @@ class EncoderStackFn(torch.autograd.Function):
                 dy1 = _dx_deep(dqkv, wqkv, tc)
                 g, dd = ln_bwd(dy1, xs, mu1, rs1, n1w, dx2, s2_prev, L, dpos, i > 0, sm(i, 0), sm(i, 1),
                                sm(i - 1, 5) if i > 0 else None, scaled_out=DD[i - 1] if i > 0 else None)
-            # ---- weight gradients of all blocks: four batched GEMMs (fp32 written by the GEMM)
-            gW2, gW1 = _wgrad_batched(DD, HH), _wgrad_batched(DPRE, Y2)
-            gWproj, gWqkv = _wgrad_batched(DA, O), _wgrad_batched(DQKV, Y1)
-            if tc:          # fc1 bias gradients of all blocks: one column-sum pass over the stacked dpre
-                small.view(depth, per)[:, 6 * C:].copy_(DPRE.sum(dim=1, dtype=torch.float32))
+                if chunked and i % GRAD_CHUNK_BLOCKS == 0:
+                    # data parallel: the weight gradients of blocks [i, i + CH) now, so their all-reduce starts now
+                    sl = slice(i, i + GRAD_CHUNK_BLOCKS)
+                    c2, c1 = _wgrad_batched(DD[sl], HH[sl]), _wgrad_batched(DPRE[sl], Y2[sl])
+                    cp, cq = _wgrad_batched(DA[sl], O[sl]), _wgrad_batched(DQKV[sl], Y1[sl])
+                    if tc:
+                        small.view(depth, per)[sl, 6 * C:].copy_(DPRE[sl].sum(dim=1, dtype=torch.float32))
+                    chunk = []
+                    for k in range(GRAD_CHUNK_BLOCKS):
+                        wg[i + k] = (cq[k], cp[k], c1[k], c2[k])
+                        chunk += block_grads(i + k, *wg[i + k])
+                    GRAD_CHUNK_HOOK(i, chunk)
+            if not chunked:
+                # ---- weight gradients of all blocks: four batched GEMMs (fp32 written by the GEMM)
+                gW2, gW1 = _wgrad_batched(DD, HH), _wgrad_batched(DPRE, Y2)
+                gWproj, gWqkv = _wgrad_batched(DA, O), _wgrad_batched(DQKV, Y1)
+                if tc:          # fc1 bias gradients of all blocks: one column-sum pass over the stacked dpre
+                    small.view(depth, per)[:, 6 * C:].copy_(DPRE.sum(dim=1, dtype=torch.float32))
+                for i in range(depth):
+                    wg[i] = (gWqkv[i], gWproj[i], gW1[i], gW2[i])
             for i in range(depth):
-                base = i * PARAMS_PER_BLOCK
-                grads[base + 0], grads[base + 1] = sm(i, 0), sm(i, 1)
-                grads[base + 2], grads[base + 3], grads[base + 4] = gWqkv[i], gWproj[i], sm(i, 2)
-                grads[base + 5], grads[base + 6] = sm(i, 3), sm(i, 4)
-                grads[base + 7], grads[base + 8] = gW1[i], sm(i, 6, Hd)
-                grads[base + 9], grads[base + 10] = gW2[i], sm(i, 5)
+                grads[i * PARAMS_PER_BLOCK:(i + 1) * PARAMS_PER_BLOCK] = block_grads(i, *wg[i])
             ctx.attn_nodes = None
-            if GRAD_READY_HOOK is not None:
+            if GRAD_READY_HOOK is not None and not chunked:
                 grads = GRAD_READY_HOOK(grads)
         gx = g.view(B, L, C) if ctx.needs_input_grad[0] else None
         gp = dpos.view(B, L, C) if ctx.needs_input_grad[1] else None

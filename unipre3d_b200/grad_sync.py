@@ -41,6 +41,8 @@ class GradSync:
             off += p.numel()
         self.overlap = bool(overlap and self.early)
         self._pending = None                       # "stream" (CUDA) or a dist.Work handle (CPU)
+        self._chunks_seen = 0                      # early parameters whose chunk all-reduce was started this backward
+        self._cpu_works = []
         self.is_cuda = self.device.type == "cuda"
         self._comm_stream = torch.cuda.Stream(device=self.device) if (self.is_cuda and self.overlap) else None
         # second communicator: the early all-reduce must not queue behind (or in front of) the SyncBatchNorm collectives
@@ -55,6 +57,10 @@ class GradSync:
             return
         if self.is_cuda:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
+        elif self._pending == "works":
+            for w in self._cpu_works:
+                w.wait()
+            self._cpu_works = []
         else:
             self._pending.wait()
         self._pending = None
@@ -74,12 +80,36 @@ class GradSync:
             self._pending = dist.all_reduce(self.flat_early, op=dist.ReduceOp.SUM, group=self._pg, async_op=True)
         return grads                              # autograd adopts the originals (no copy); finish() re-points p.grad
 
+    def early_chunk_hook(self, first_param: int, grads) -> None:
+        """grads: gradients of early parameters [first_param, first_param + len(grads)) (early_params order), complete
+        while the backward is still running: pack them and start the all-reduce of their slice of the flat buffer."""
+        if not self.overlap:
+            return
+        if self._chunks_seen == 0:
+            self._join()                          # a previous backward that was never consumed
+        views = self._early_views()[first_param:first_param + len(grads)]
+        torch._foreach_copy_(views, list(grads))
+        a, b = self._early_slices[first_param][0], self._early_slices[first_param + len(grads) - 1][1]
+        if self.is_cuda:
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self._pg)
+            self._pending = "stream"
+        else:
+            w = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self._pg, async_op=True)
+            self._cpu_works.append(w)
+            self._pending = "works"
+        self._chunks_seen += len(grads)
+
     def finish(self) -> None:
         if any(p.grad is None for p in self.early + self.rest):
             raise RuntimeError("a trainable parameter received no gradient (data-parallel ranks would diverge)")
+        if self._chunks_seen not in (0, len(self.early)):
+            raise RuntimeError("chunked gradient exchange covered only part of the early parameters")
         if self._pending is None and self.early:  # the hook did not fire (module path / overlap off): reduce it now
             torch._foreach_copy_(self._early_views(), [p.grad for p in self.early])
             dist.all_reduce(self.flat_early, op=dist.ReduceOp.SUM)
+        self._chunks_seen = 0
         if self.rest:
             torch._foreach_copy_(self._rest_views, [p.grad for p in self.rest])
             dist.all_reduce(self.flat_rest, op=dist.ReduceOp.SUM)

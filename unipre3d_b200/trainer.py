@@ -64,6 +64,55 @@ def shard_batch(data, rank: int, world: int):
     return {k: ({kk: cut(vv) for kk, vv in v.items()} if isinstance(v, dict) else cut(v)) for k, v in data.items()}
 
 
+def _flat_items(data, prefix=""):
+    for k in sorted(data.keys()):
+        v = data[k]
+        if isinstance(v, dict):
+            yield from _flat_items(v, prefix + k + "/")
+        elif torch.is_tensor(v):
+            yield prefix + k, v
+
+
+class PackedBatch:
+    """A batch dict whose tensors are views into ONE pinned host buffer (256-byte aligned slots), so that a step moves its
+    inputs with one host->device copy and one device->device copy instead of one pair per tensor.  `Trainer.pack_batch`
+    builds it from an ordinary batch dict; a data loader can also fill `packed.data` in place (no extra host copy)."""
+
+    def __init__(self, data, pin: bool = True):
+        self.layout, off = [], 0
+        for name, t in _flat_items(data):
+            nbytes = t.numel() * t.element_size()
+            self.layout.append((name, off, tuple(t.shape), t.dtype, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self.nbytes = off
+        self.flat = torch.empty(off, dtype=torch.uint8)
+        if pin and torch.cuda.is_available():
+            self.flat = self.flat.pin_memory()
+        self.data = self.views(self.flat)
+        for name, t in _flat_items(data):
+            self._get(self.data, name).copy_(t)
+
+    def views(self, flat):
+        """The batch dict as views into `flat` (a uint8 buffer of self.nbytes bytes on any device)."""
+        out = {}
+        for name, off, shape, dtype, nbytes in self.layout:
+            v = flat[off:off + nbytes].view(dtype).view(shape)
+            d, parts = out, name.split("/")
+            for p_ in parts[:-1]:
+                d = d.setdefault(p_, {})
+            d[parts[-1]] = v
+        return out
+
+    @staticmethod
+    def _get(d, name):
+        for p_ in name.split("/"):
+            d = d[p_]
+        return d
+
+    def signature(self):
+        return tuple((n, s, str(dt)) for n, _, s, dt, _ in self.layout)
+
+
 class EMA:
     """Exponential moving average of the model weights with ema_pytorch's default schedule (the reference
     wraps the model in ema_pytorch.EMA(beta, update_every, update_after_step), train_network.py:188-198):
@@ -260,6 +309,7 @@ class Trainer:
         else:
             from . import fused_encoder
             fused_encoder.GRAD_READY_HOOK = None      # a hook left by an earlier data-parallel Trainer of this process
+            fused_encoder.GRAD_CHUNK_HOOK = None
         self.iteration = 0
         self._graph = None
         self._static: Optional[dict] = None
@@ -274,7 +324,9 @@ class Trainer:
         self._loss_ev = [None, None]
         # input pipelining: the next batch is copied host->device on a side stream while the current step runs
         self._copy_stream = torch.cuda.Stream(device=self.device)
-        self._staged = None          # (key, device dict, ready event)
+        self._staged = None          # (key, device dict | flat device buffer, ready event)
+        self._stage_flat = None      # device image of the PackedBatch being prefetched
+        self._static_flat = None     # flat device buffer behind the captured graph's static inputs
 
     def _lpips_due(self, iteration: int) -> bool:
         """train_network.py:229-231, 288-296: the LPIPS term joins the loss after opt.start_lpips_after."""
@@ -285,7 +337,7 @@ class Trainer:
         captured graph (parameter / moment / pointer tables) is dropped and re-captured at the next iteration."""
         info = self.model_manager.load_checkpoint(path, load_optimizer=load_optimizer)
         self.iteration = info["iteration"]
-        self._graph, self._static, self._staged = None, None, None
+        self._graph, self._static, self._staged, self._static_flat = None, None, None, None
         return info
 
     # ---------------------------------------------------------------------------------------------
@@ -331,6 +383,11 @@ class Trainer:
         self.model_manager.optimizer.grad_scale = 1.0 / self.world
         if self._grad_sync.overlap:
             fused_encoder.GRAD_READY_HOOK = self._grad_sync.early_hook
+            if not os.environ.get("UP3D_NO_CHUNKED_SYNC"):
+                # blocks' gradients leave in chunks of GRAD_CHUNK_BLOCKS while the backward of earlier blocks still runs
+                per = fused_encoder.PARAMS_PER_BLOCK
+                gs = self._grad_sync
+                fused_encoder.GRAD_CHUNK_HOOK = lambda first_block, grads: gs.early_chunk_hook(first_block * per, grads)
 
     def _allreduce_grads(self) -> None:
         """N > 1: SUM the gradients over ranks (the optimizer applies 1/world) and point every p.grad at its slice of
@@ -391,6 +448,12 @@ class Trainer:
 
     # ---------------------------------------------------------------------------------------------
     def _copy_into_static(self, data) -> None:
+        if torch.is_tensor(data):                                       # flat device image of a PackedBatch
+            if self._static_flat is None:
+                raise RuntimeError("the step graph was captured from an unpacked batch; pass the same kind every step")
+            self._static_flat.copy_(data, non_blocking=True)            # ONE device->device copy
+            return
+
         def cp(dst, src):
             if isinstance(dst, dict):
                 for k in dst:
@@ -399,13 +462,23 @@ class Trainer:
                 dst.copy_(src, non_blocking=True)
         cp(self._static, data)
 
+    def pack_batch(self, data) -> PackedBatch:
+        """Host batch dict -> PackedBatch (one flat pinned buffer): the form `train_iteration` moves with ONE H2D copy."""
+        return PackedBatch(data)
+
     def _stage(self, data) -> None:
-        """Start the H2D copy of `data` (pinned host dict) on the copy stream."""
+        """Start the H2D copy of `data` (pinned host dict or PackedBatch) on the copy stream."""
         if self._staged is not None and self._staged[0] is data:
             return
         self._copy_stream.wait_stream(torch.cuda.current_stream())   # staging buffers may still be read
         with torch.cuda.stream(self._copy_stream):
-            dev = _to_device(data, self.device, non_blocking=True)
+            if isinstance(data, PackedBatch):
+                if self._stage_flat is None or self._stage_flat.numel() != data.nbytes:
+                    self._stage_flat = torch.empty(data.nbytes, dtype=torch.uint8, device=self.device)
+                self._stage_flat.copy_(data.flat, non_blocking=True)            # ONE host->device copy
+                dev = self._stage_flat
+            else:
+                dev = _to_device(data, self.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         self._staged = (data, dev, ev)
@@ -416,11 +489,16 @@ class Trainer:
             _, dev, ev = self._staged
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
+            if torch.is_tensor(dev):                                    # flat staging buffer of a PackedBatch
+                self._staged = None
+                return dev
             for t in (list(dev["point_cloud"].values()) if isinstance(dev.get("point_cloud"), dict) else []) + \
                     [v for v in dev.values() if torch.is_tensor(v)]:
                 t.record_stream(cur)     # allocated on the copy stream, consumed on the compute stream
             self._staged = None
             return dev
+        if isinstance(data, PackedBatch):
+            return data.flat.to(self.device, non_blocking=True)
         return _to_device(data, self.device)
 
     def train_iteration(self, data, read_loss: bool = True, prefetch=None):
@@ -434,12 +512,20 @@ class Trainer:
             raise NotImplementedError("LPIPS loss needs VGG weights (not shipped); set opt.lambda_lpips=0")
         if not self.use_cuda_graph:
             dev = self._take_staged(data)
+            if torch.is_tensor(dev):
+                dev = data.views(dev.clone())       # eager mode: the staging buffer is rewritten by the next prefetch
             if prefetch is not None:
                 self._stage(prefetch)
             loss = self._step_body(dev)
         else:
             if self._static is None:
-                self._static = _to_device(data, self.device, non_blocking=False)
+                if isinstance(data, PackedBatch):
+                    # static inputs = views into one flat device buffer (refreshed by a single copy per step)
+                    self._static_flat = data.flat.to(self.device)
+                    self._static = data.views(self._static_flat)
+                    self._static_sig = data.signature()
+                else:
+                    self._static = _to_device(data, self.device, non_blocking=False)
                 # warm-up on a side stream (allocator, cuBLAS handles, layout cache, lazy grads), then capture.  The
                 # warm-up steps are real optimizer steps on the first batch: model, BatchNorm buffers, optimizer
                 # moments and the step counter are snapshotted and put back, so iteration 1 starts from the same state
@@ -456,6 +542,8 @@ class Trainer:
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
                     self._loss_buf.copy_(self._step_body(self._static))
+            if isinstance(data, PackedBatch) and getattr(self, "_static_sig", None) != data.signature():
+                raise RuntimeError("PackedBatch layout differs from the one the step graph was captured with")
             self._copy_into_static(self._take_staged(data))     # D2D when prefetched, H2D otherwise
             if prefetch is not None:
                 self._stage(prefetch)
