@@ -307,3 +307,51 @@ def test_packed_batch_is_one_buffer_with_aligned_views():
     for k in ("world_view_transforms", "full_proj_transforms", "view_to_world_transforms", "camera_centers"):
         assert torch.equal(mirror[k], b[k])
     assert PackedBatch(b, pin=False).signature() == p.signature()
+
+
+def test_scene_level_output_processing_matches_reference_loop():
+    """GaussianSplatPredictor._process_network_output_scene == the mask loop of model/gaussian_predictor.py:331-364."""
+    from types import SimpleNamespace as NS
+    from unipre3d_b200.gaussian_predictor import GaussianSplatPredictor
+    m = GaussianSplatPredictor.__new__(GaussianSplatPredictor)
+    torch.nn.Module.__init__(m)
+    m.cfg = NS(model=NS(max_sh_degree=1, isotropic=False, offset_scale=0.2))
+    g = torch.Generator().manual_seed(0)
+    n = 50
+    raw = torch.randn(n, 23, generator=g)
+    coord = torch.randn(n, 3, generator=g)
+    batch = torch.sort(torch.randint(0, 3, (n,), generator=g))[0]
+    indices = torch.cat([batch[:, None], torch.randint(0, 100, (n, 3), generator=g)], 1).int()
+    out = m._process_network_output_scene(raw.split([3, 1, 3, 4, 3, 9], dim=1), coord, indices)
+    xyz_raw, opacity, scaling, rotation, dc, rest = raw.split([3, 1, 3, 4, 3, 9], dim=1)
+    pos = torch.tanh(xyz_raw) * 0.2 + coord
+    for b in range(3):
+        mask = indices[:, 0] == b
+        assert torch.allclose(out["xyz"][b], pos[mask])
+        assert torch.allclose(out["opacity"][b], torch.sigmoid(opacity[mask]))
+        assert torch.allclose(out["scaling"][b], torch.exp(torch.clamp(scaling[mask], -1, 20)))
+        assert torch.allclose(out["rotation"][b], torch.nn.functional.normalize(rotation[mask], dim=-1, eps=1e-6))
+        assert torch.equal(out["features_dc"][b], dc[mask].unsqueeze(1))
+        # _process_sh_features: (n, 9) -> reshape(n, 9, 1).permute(0, 2, 1).reshape(n, -1, 3)
+        fr = rest[mask]
+        ref = fr.reshape(fr.shape[0], fr.shape[1], -1).permute(0, 2, 1).reshape(fr.shape[0], -1, 3)
+        assert torch.equal(out["features_rest"][b], ref) and ref.shape[1:] == (3, 3)
+
+
+def test_scene_configs_compose_and_synthetic_scene_batch():
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.config import compose
+    for name, bb in (("sparseunet_pretraining", "sparseunet"), ("ptv3_pretraining", "ptv3")):
+        cfg = compose(name)
+        assert cfg.model.backbone_type == bb and cfg.opt.level == "scene" and cfg.data.training_width == 160
+        assert cfg.data.znear == 0.2 and cfg.data.zfar == 10 and cfg.data.white_background is True and cfg.opt.loss == "l2"
+    cfg = compose("sparseunet_pretraining", overrides=["data.input_images=2", "opt.imgs_per_obj=2"])
+    b = synthetic.make_scene_batch(cfg, 2, 5000, seed=1)
+    pc = b["point_cloud"]
+    assert pc["offset"].tolist()[-1] == pc["coord"].shape[0] == pc["grid_coord"].shape[0] == pc["feat"].shape[0]
+    assert pc["feat"].shape[1] == 6 and int(pc["grid_coord"].min()) == 0
+    assert b["gt_images"].shape == (2, 4, 3, 120, 160)
+    key = (pc["grid_coord"][: pc["offset"][0]].long() * torch.tensor([1 << 40, 1 << 20, 1])).sum(1)
+    assert key.unique().numel() == key.numel(), "one point per voxel"
+    wv, vw = b["world_view_transforms"][1, 2], b["view_to_world_transforms"][1, 2]
+    assert torch.allclose(wv @ vw, torch.eye(4), atol=1e-5)

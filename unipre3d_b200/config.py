@@ -74,11 +74,27 @@ _TRANSFORMER = {
 }
 _POINTMLP = copy.deepcopy(_TRANSFORMER)
 _POINTMLP["model"].update({"backbone_type": "pointmlp", "in_channels": 4})
+# configs/dataset/scannet.yaml + configs/sparseunet_pretraining.yaml / ptv3_pretraining.yaml of the reference
+_SCANNET = {"data": {"znear": 0.2, "zfar": 10, "category": "scannet", "white_background": True, "use_neighbor_imgs": True,
+                     "use_self_supervise": False, "supervised_max_distance": 5,
+                     "pts_dataset_root": "/path/to/scannet/dataset", "rgb_dataset_root": "/path/to/scannet/color"}}
+_SPARSEUNET = {
+    "general": {"cuda": True, "device": [0, 1, 2, 3], "random_seed": 42},
+    "data": {"fov": 57.9516132895, "training_width": 160, "training_height": 120, "input_images": 8},
+    "model": {"backbone_type": "sparseunet", "in_channels": 3, "aug": False, "offset_scale": 0.2},
+    "opt": {"iterations": 60000, "mode": "train", "level": "scene", "use_fusion": True, "base_lr": 0.0001, "batch_size": 4,
+            "test_generation_num": 1, "loss": "l2", "step_lr": 10000, "lr_gamma": 0.9, "start_lpips_after": 30000},
+}
+_PTV3 = copy.deepcopy(_SPARSEUNET)
+_PTV3["model"].update({"backbone_type": "ptv3"})
 BUILTIN = {
     "settings": _SETTINGS,
     "dataset/shapenet": _SHAPENET,
     "transformer_pretraining": {"defaults": ["/settings@_here_", "/dataset/shapenet@_here_"], **_TRANSFORMER},
     "pointmlp_pretraining": {"defaults": ["/settings@_here_", "/dataset/shapenet@_here_"], **_POINTMLP},
+    "dataset/scannet": _SCANNET,
+    "sparseunet_pretraining": {"defaults": ["/settings@_here_", "/dataset/scannet@_here_"], **_SPARSEUNET},
+    "ptv3_pretraining": {"defaults": ["/settings@_here_", "/dataset/scannet@_here_"], **_PTV3},
     "default_config": {"defaults": ["/transformer_pretraining@_here_"]},
 }
 

@@ -156,10 +156,14 @@ class PointFeaturePredictor(nn.Module):
             from .pointmlp import pointMLP
             self.encoder = pointMLP(cfg=cfg)
             self.final = nn.Sequential(nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 23))
+        elif model_type == "sparseunet":
+            from .sparse_unet import SpUNetBase
+            self.encoder = SpUNetBase(in_channels=6, num_classes=64, cfg=cfg)          # point_predictor.py:64-67
+            self.final = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 23))
         else:
             raise NotImplementedError(
-                f"backbone_type={model_type!r}: 'transformer' (SURVEY.md §8a rows B1-B5) and 'pointmlp' (row B6) are "
-                "built; ptv3/sparseunet are rows P1/P2 (need a sparse-conv engine), pcm/mamba3d are out of scope")
+                f"backbone_type={model_type!r}: 'transformer' (SURVEY.md §8a rows B1-B5), 'pointmlp' (row B6) and "
+                "'sparseunet' (row P2) are built; ptv3 is row P1, pcm/mamba3d are out of scope")
         if pretrained_path is not None:
             info = self.load_state_dict(torch.load(pretrained_path), strict=False)
             print(f"Loaded pretrained weights from {pretrained_path}")
@@ -173,6 +177,19 @@ class PointFeaturePredictor(nn.Module):
     def forward_feat_fusion(self, x, image_features, c2w_projection_matrix, fusion_mlps, intrinsic):
         x, center = self.encoder.forward(x, image_features, c2w_projection_matrix, fusion_mlps, intrinsic)
         return self.final(x).permute(0, 2, 1), center
+
+    def forward_point_fusion(self, x, image_features, unprojected_coords, fusion_mlps):
+        """point_predictor.py:117-134 (scene level): -> (per-point head outputs (n, 23), indices (n, 4) = (batch, grid
+        coord)), both in the order of the INPUT points (the sparse tensor keeps voxels sorted internally)."""
+        out = self.encoder.forward(x, image_features, unprojected_coords, fusion_mlps)
+        feats = self.final(out.features)
+        if out.perm is not None:
+            unsorted = torch.empty_like(feats)
+            unsorted[out.perm] = feats
+            idx = torch.empty_like(out.indices)
+            idx[out.perm] = out.indices
+            return unsorted, idx
+        return feats, out.indices
 
 
 class GaussianSplatPredictor(nn.Module):
@@ -190,10 +207,16 @@ class GaussianSplatPredictor(nn.Module):
         self.split_dimensions = [3, 1, 3, 4, 3]
         if cfg.model.max_sh_degree != 0:
             self.split_dimensions.append(((cfg.model.max_sh_degree + 1) ** 2 - 1) * 3)
-        if cfg.opt.level != "object":
-            raise NotImplementedError("opt.level='scene' (SURVEY.md §8a rows P1/P2) needs the sparse-conv backbones")
         pretrained = getattr(cfg.opt, "pretrained_ckpt", None)
-        if self.use_fusion:
+        if cfg.opt.level != "object":
+            if cfg.opt.level != "scene":
+                raise ValueError("Invalid optimization level")
+            if self.use_fusion:
+                raise NotImplementedError(
+                    "opt.level='scene' with opt.use_fusion=true needs PointFusion (fusion/point_fusion.py:36-131: CPU/numpy "
+                    "GridSample voxeliser), which is not built; run the scene backbones with opt.use_fusion=false")
+            self.point_network = PointFeaturePredictor(cfg, self.split_dimensions, pretrained_path=pretrained)
+        elif self.use_fusion:
             # image branch: "stem" (default) = weight-free analytic stand-in; "sdvae" = the reference's frozen
             # Stable-Diffusion VAE architecture (image_predictor.py; random-init unless model.vae_weights names the
             # reference's weights/diffusion_pytorch_model.bin)
@@ -249,6 +272,11 @@ class GaussianSplatPredictor(nn.Module):
         return self._forward_basic(point_cloud, source_cameras_view_to_world)
 
     def _forward_basic(self, point_cloud, source_cameras_view_to_world):
+        if self.cfg.opt.level == "scene":
+            # gaussian_predictor.py:157-167 without the image fusion: backbone -> final -> per-scene lists
+            point_features, indices = self.point_network.forward_point_fusion(point_cloud, None, None, None)
+            return self._process_network_output_scene(point_features.split(self.split_dimensions, dim=1),
+                                                      point_cloud["coord"], indices)
         point_output, center = self.point_network(point_cloud)
         out = self._process_network_output(point_output.split(self.split_dimensions, dim=1), center)
         return {k: v.contiguous() for k, v in out.items()}
@@ -293,6 +321,34 @@ class GaussianSplatPredictor(nn.Module):
     @staticmethod
     def _flatten_vector(x):
         return x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+
+    def _process_network_output_scene(self, network_output: List[torch.Tensor], center, indices):
+        """Scene branch of gaussian_predictor.py:298-364: inputs are (n, C) rows of ALL scenes, output values are lists
+        with one (n_b, ...) tensor per scene; quaternions are normalised per point here (the (n, 4) layout makes
+        F.normalize(dim=-1) the usual unit-quaternion normalisation, unlike the object branch)."""
+        xyz_raw, opacity, scaling, rotation, features_dc = network_output[:5]
+        pos = self.pos_act(xyz_raw) * self.cfg.model.offset_scale + center[:, :3]
+        if self.cfg.model.isotropic:
+            scaling = scaling[:, :1].expand(-1, 3)
+        batch = indices[:, 0].long()
+        counts = torch.bincount(batch).tolist()              # one host read per step (the reference reads .max().item())
+        keys = ("xyz", "opacity", "scaling", "rotation", "features_dc", "features_rest")
+        out = {k: [None] * len(counts) for k in keys}
+        order = torch.argsort(batch, stable=True)            # scenes are contiguous in the loaders; stable = no-op then
+        M1 = (self.cfg.model.max_sh_degree + 1) ** 2 - 1
+        vals = {"xyz": pos, "opacity": self.opacity_activation(opacity), "scaling": self.scaling_activation(scaling),
+                "rotation": self.rotation_activation(rotation), "features_dc": features_dc.unsqueeze(1)}
+        if self.cfg.model.max_sh_degree > 0:
+            vals["features_rest"] = network_output[5].reshape(network_output[5].shape[0], -1, 3)
+        else:
+            vals["features_rest"] = torch.zeros((pos.shape[0], M1, 3), dtype=pos.dtype, device=pos.device)
+        start = 0
+        for b, c in enumerate(counts):
+            sel = order[start:start + c]
+            for k in keys:
+                out[k][b] = vals[k][sel]
+            start += c
+        return out
 
     def _process_network_output(self, network_output: List[torch.Tensor], center) -> Dict[str, torch.Tensor]:
         """Object branch of gaussian_predictor.py:279-328."""

@@ -79,6 +79,66 @@ def make_batch(cfg, batch_size: int, n_points: int, seed: int = 0, pin: bool = F
     return batch
 
 
+def make_scene_batch(cfg, n_scenes: int, n_points: int, seed: int = 0, grid_size: float = 0.02,
+                     room=(8.0, 6.0, 3.0)) -> Dict[str, torch.Tensor]:
+    """ScanNet-shaped synthetic scenes: per scene `n_points` surface points of a room-sized box
+    (floor, walls, a few boxes), voxelised at `grid_size` (first point per voxel kept, as GridSample's test mode),
+    cameras inside the room looking around; the dict pointcept's collate emits ("coord", "grid_coord", "feat", "offset")
+    plus the camera matrices / images of the object-level loader (row-vector, transposed matrices)."""
+    rng = np.random.default_rng(seed)
+    V = int(cfg.data.input_images) + int(cfg.opt.imgs_per_obj)
+    H, W = (int(cfg.data.training_height), int(cfg.data.training_width)) if hasattr(cfg.data, "training_height") else \
+        (int(cfg.data.training_resolution),) * 2
+    fovx = math.radians(cfg.data.fov)
+    fovy = 2 * math.atan(math.tan(fovx / 2) * H / W)
+    proj_t = cam.get_projection_matrix(cfg.data.znear, cfg.data.zfar, fovx, fovy).transpose(0, 1)       # row-vector form
+    rx, ry, rz = room
+    coords, grids, feats, offsets, gts, v2w_all = [], [], [], [], [], []
+    total = 0
+    bgc = 1.0 if cfg.data.white_background else 0.0
+    for _ in range(n_scenes):
+        # surfaces: floor (40 %), four walls (40 %), three boxes (20 %)
+        n_f, n_w = int(0.4 * n_points), int(0.4 * n_points)
+        pts = [np.stack([rng.uniform(0, rx, n_f), rng.uniform(0, ry, n_f), np.zeros(n_f)], 1)]
+        wall = rng.integers(0, 4, n_w)
+        u, h = rng.uniform(0, 1, n_w), rng.uniform(0, rz, n_w)
+        wx = np.where(wall == 0, 0.0, np.where(wall == 1, rx, u * rx))
+        wy = np.where(wall == 2, 0.0, np.where(wall == 3, ry, u * ry))
+        pts.append(np.stack([wx, wy, h], 1))
+        n_b = n_points - n_f - n_w
+        centre = rng.uniform([1, 1, 0.3], [rx - 1, ry - 1, 0.9], (3, 3))[rng.integers(0, 3, n_b)]
+        pts.append(centre + rng.uniform(-0.4, 0.4, (n_b, 3)) * np.array([1, 1, 0.7]))
+        p = np.concatenate(pts, 0).astype(np.float32)
+        g = np.floor(p / grid_size).astype(np.int64)
+        g -= g.min(0, keepdims=True)
+        _, first = np.unique((g[:, 0] * 4096 + g[:, 1]) * 4096 + g[:, 2], return_index=True)
+        first.sort()
+        p, g = p[first], g[first]
+        color = rng.uniform(0, 1, (p.shape[0], 3)).astype(np.float32)
+        coords.append(p)
+        grids.append(g.astype(np.int32))
+        feats.append(np.concatenate([color, p / np.array(room, np.float32)], 1).astype(np.float32))     # 6 input channels
+        total += p.shape[0]
+        offsets.append(total)
+        views = []
+        for _v in range(V):
+            R, t = cam.look_at_pose(rng.uniform(-180, 180), rng.uniform(-5, 25), 1.0)     # orientation only
+            v2w = torch.tensor(cam.get_view2world(R, t)).transpose(0, 1).float().clone()
+            v2w[3, :3] = torch.tensor(rng.uniform([2, 2, 1.2], [rx - 2, ry - 2, 1.8]), dtype=torch.float32)   # eye in the room
+            views.append(v2w)
+        v2w_all.append(torch.stack(views))
+        gts.append(np.where(rng.uniform(0, 1, (V, 1, H, W)) < 0.7, rng.uniform(0, 1, (V, 3, H, W)), bgc).astype(np.float32))
+    v2w = torch.stack(v2w_all)
+    w2v = torch.linalg.inv(v2w)
+    batch = {"view_to_world_transforms": v2w, "world_view_transforms": w2v, "full_proj_transforms": w2v @ proj_t,
+             "camera_centers": v2w[:, :, 3, :3].clone(), "gt_images": torch.from_numpy(np.stack(gts)),
+             "point_cloud": {"coord": torch.from_numpy(np.concatenate(coords)),
+                             "grid_coord": torch.from_numpy(np.concatenate(grids)),
+                             "feat": torch.from_numpy(np.concatenate(feats)),
+                             "offset": torch.tensor(offsets, dtype=torch.int64)}}
+    return batch
+
+
 def batch_nbytes(batch) -> int:
     n = 0
     for v in batch.values():
