@@ -1,0 +1,62 @@
+"""PointTransformerV3 module mirror (unipre3d_b200/ptv3.py) on CUDA against a fixture produced by the REFERENCE's own
+PointTransformerV3 code (tests/golden/make_golden_ptv3.py: reference files unmodified, spconv replaced by the dense-grid
+oracle with the kernels' bf16 operand rounding, exact attention branch).  Differences left: fp32 (device) vs fp64 (oracle)
+accumulation inside the sparse convolutions in front of bf16 roundings, summation order in Linear / attention.
+Tolerance 2e-2 of the output scale (measured ~2e-3); serialization order, pooling clusters and padding must be identical
+(otherwise the outputs differ at O(1))."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _net_and_data():
+    from types import SimpleNamespace as NS
+    from unipre3d_b200.ptv3 import PointTransformerV3
+    z = np.load(os.path.join(G, "ptv3_small.npz"))
+    kw = ast.literal_eval(str(z["cfg_json"]))
+    net = PointTransformerV3(cfg=NS(opt=NS(use_fusion=False)), **kw)
+    sd = {k[3:]: torch.tensor(z[k]) for k in z.files if k.startswith("sd.")}
+    info = net.load_state_dict(sd, strict=True)          # same parameter names / layouts as the reference module
+    assert not info.missing_keys and not info.unexpected_keys
+    data = {k: torch.tensor(z[k]).cuda() for k in ("coord", "grid_coord", "feat", "offset")}
+    return net.cuda().train(), data, z
+
+
+def test_ptv3_forward_matches_reference_fixture():
+    net, data, z = _net_and_data()
+    with torch.no_grad():
+        point = net(data)
+    assert point.feat.shape == z["out_feat"].shape
+    assert np.array_equal(point.batch.cpu().numpy(), z["out_batch"])
+    np.testing.assert_allclose(point.coord.cpu().numpy(), z["out_coord"], atol=1e-6)
+    err = np.abs(point.feat.cpu().numpy() - z["out_feat"]).max()
+    assert err <= 2e-2 * np.abs(z["out_feat"]).max(), (err, np.abs(z["out_feat"]).max())
+
+
+def test_ptv3_trains_and_flash_branch_is_close():
+    net, data, z = _net_and_data()
+    ref = torch.tensor(z["out_feat"]).cuda()
+    # fused-attention branch (bf16 SDPA over the padded patches) stays close to the exact branch
+    for m in net.modules():
+        if m.__class__.__name__ == "SerializedAttention":
+            m.enable_flash, m.patch_size, m.attn_drop = True, m.patch_size_max, 0.0
+    with torch.no_grad():
+        fast = net({k: v.clone() for k, v in data.items()}).feat
+    assert float((fast - ref).abs().max()) <= 0.1 * float(ref.abs().max())
+    opt = torch.optim.SGD(net.parameters(), lr=0.02)
+    target = torch.randn_like(ref)
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        loss = ((net({k: v.clone() for k, v in data.items()}).feat - target) ** 2).mean()
+        loss.backward()
+        assert all(p.grad is None or torch.isfinite(p.grad).all() for p in net.parameters())
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses

@@ -27,3 +27,18 @@ def test_sparseunet_scene_step_runs_and_learns():
     assert float((out["xyz"][0] - dev["point_cloud"]["coord"][: sizes[0]]).abs().max()) <= 0.2 + 1e-5
     losses = [tr.train_iteration(data) for _ in range(5)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+
+
+def test_ptv3_scene_step_runs_and_learns():
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.config import compose
+    from unipre3d_b200.trainer import Trainer
+    cfg = compose("ptv3_pretraining", overrides=["opt.use_fusion=false", "data.input_images=2", "opt.imgs_per_obj=2",
+                                                  "opt.batch_size=2", "opt.ema.use=false"])
+    tr = Trainer(cfg, use_cuda_graph=False)
+    for m in tr.model_manager.model.modules():
+        if m.__class__.__name__ == "DropPath":
+            m.drop_prob = 0.0
+    data = synthetic.make_scene_batch(cfg, 2, 5000, seed=3)
+    losses = [tr.train_iteration(data) for _ in range(5)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses

@@ -160,10 +160,14 @@ class PointFeaturePredictor(nn.Module):
             from .sparse_unet import SpUNetBase
             self.encoder = SpUNetBase(in_channels=6, num_classes=64, cfg=cfg)          # point_predictor.py:64-67
             self.final = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 23))
+        elif model_type == "ptv3":
+            from .ptv3 import PointTransformerV3
+            self.encoder = PointTransformerV3(in_channels=6, cfg=cfg)                   # point_predictor.py:68-69
+            self.final = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 23))
         else:
             raise NotImplementedError(
-                f"backbone_type={model_type!r}: 'transformer' (SURVEY.md §8a rows B1-B5), 'pointmlp' (row B6) and "
-                "'sparseunet' (row P2) are built; ptv3 is row P1, pcm/mamba3d are out of scope")
+                f"backbone_type={model_type!r}: 'transformer' (SURVEY.md §8a rows B1-B5), 'pointmlp' (row B6), 'sparseunet' "
+                "(row P2) and 'ptv3' (row P1) are built; pcm/mamba3d are out of scope")
         if pretrained_path is not None:
             info = self.load_state_dict(torch.load(pretrained_path), strict=False)
             print(f"Loaded pretrained weights from {pretrained_path}")
@@ -182,6 +186,9 @@ class PointFeaturePredictor(nn.Module):
         """point_predictor.py:117-134 (scene level): -> (per-point head outputs (n, 23), indices (n, 4) = (batch, grid
         coord)), both in the order of the INPUT points (the sparse tensor keeps voxels sorted internally)."""
         out = self.encoder.forward(x, image_features, unprojected_coords, fusion_mlps)
+        if self.cfg.model.backbone_type.lower() == "ptv3":                              # point_predictor.py:128-132
+            st = out.sparse_conv_feat
+            return self.final(st.features), st.indices
         feats = self.final(out.features)
         if out.perm is not None:
             unsorted = torch.empty_like(feats)

@@ -33,8 +33,18 @@ def pack_keys(indices: torch.Tensor) -> torch.Tensor:
 class SparseConvTensor:
     """features (n, C) fp32, indices (n, 4) int32 (batch, c0, c1, c2), sorted by key."""
 
-    def __init__(self, features, indices, spatial_shape=None, batch_size=None, _sorted=False, _rules=None, _perm=None):
-        if not _sorted:
+    def __init__(self, features, indices, spatial_shape=None, batch_size=None, _sorted=False, _rules=None, _perm=None,
+                 keep_order=False):
+        """keep_order=True: rows stay in the caller's order (PTv3 keeps `point.feat` and the sparse tensor row-aligned);
+        the sorted keys are kept on the side for rulebook construction.  Only SubMConv3d accepts such tensors."""
+        self.keep_order = bool(keep_order)
+        if keep_order:
+            keys, perm = torch.sort(pack_keys(indices))
+            if keys.numel() > 1 and bool((keys[1:] == keys[:-1]).any()):
+                raise ValueError("duplicate voxel coordinates")
+            self.perm, self.keys = perm, keys
+            self.sorted_indices = indices.int()[perm].contiguous()
+        elif not _sorted:
             keys = pack_keys(indices)
             keys, perm = torch.sort(keys)
             if keys.numel() > 1 and bool((keys[1:] == keys[:-1]).any()):
@@ -48,6 +58,8 @@ class SparseConvTensor:
             self.keys = (i[:, 0] << 48) | (i[:, 1] << 32) | (i[:, 2] << 16) | i[:, 3]
         self.features = features
         self.indices = indices.int().contiguous()
+        if not hasattr(self, "keep_order"):
+            self.keep_order = False
         self.spatial_shape, self.batch_size = spatial_shape, batch_size
         self.rules: Dict[str, dict] = _rules if _rules is not None else {}
 
@@ -59,7 +71,7 @@ class SparseConvTensor:
 
     def features_in_input_order(self):
         """Rows in the order the constructor received them (inverse of the sort)."""
-        if self.perm is None:
+        if self.perm is None or self.keep_order:
             return self.features
         out = torch.empty_like(self.features)
         out[self.perm] = self.features
@@ -75,8 +87,15 @@ def subm_rulebook(x: SparseConvTensor, k: int) -> torch.Tensor:
     require_cuda(x.features)
     n = x.n
     nbr = torch.empty((k ** 3, n), dtype=torch.int32, device=x.features.device)
+    sidx = x.sorted_indices if x.keep_order else x.indices
     with torch.cuda.device(x.features.device):
-        check(_lib.lib.up3d_sparse_subm_rulebook(n, k, ptr(x.keys), ptr(x.indices), ptr(nbr), stream_ptr()), launches=1)
+        check(_lib.lib.up3d_sparse_subm_rulebook(n, k, ptr(x.keys), ptr(sidx), ptr(nbr), stream_ptr()), launches=1)
+    if x.keep_order:
+        # sorted positions -> caller's rows: values through perm (-1 stays -1), columns scattered to row perm[s]
+        perm_ext = torch.cat([x.perm.int(), x.perm.new_full((1,), -1).int()])
+        rows = perm_ext[nbr.long()]
+        nbr = torch.empty_like(rows)
+        nbr[:, x.perm] = rows
     return nbr
 
 
@@ -203,6 +222,8 @@ class SparseConv3d(_SparseConvBase):
         super().__init__(in_channels, out_channels, kernel_size, bias, indice_key)
 
     def forward(self, x: SparseConvTensor) -> SparseConvTensor:
+        if x.keep_order:
+            raise NotImplementedError("SparseConv3d needs a sorted SparseConvTensor (keep_order=False)")
         cidx, nbr_down, nbr_up = downsample_rule(x)
         out = SparseConvFn.apply(x.features, self._w_kio(), nbr_down, nbr_up, int(cidx.shape[0]))
         shape = None if x.spatial_shape is None else [(s + 1) // 2 for s in x.spatial_shape]
