@@ -377,6 +377,10 @@ UP3D_API int up3d_fusion_project(int B, int N, int H, int W, int C, int G, float
  * ---------------------------------------------------------------------------------------- */
 UP3D_API int up3d_zorder_keys(int64_t n, int depth, int swap_xy, const int32_t *grid_coord, const int64_t *batch, int64_t *code,
                               up3d_stream_t stream);
+/* same interface for the "hilbert" / "hilbert-trans" orders (serialization/hilbert.py:96-191: Skilling's transpose,
+ * bit interleave with dimension 0 most significant, Gray decode). */
+UP3D_API int up3d_hilbert_keys(int64_t n, int depth, int swap_xy, const int32_t *grid_coord, const int64_t *batch, int64_t *code,
+                               up3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Frozen image stem (stand-in for model/image_predictor.py:56-81, whose SD-VAE weights are not shipped):

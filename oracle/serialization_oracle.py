@@ -22,12 +22,43 @@ def z_order_key(x, y, z, depth: int = 16) -> np.ndarray:
     return key
 
 
+def hilbert_key(x, y, z, depth: int) -> np.ndarray:
+    """serialization/hilbert.py:96-191 (Skilling's transpose on integers instead of bit planes): per bit from the top and
+    per dimension, invert the lower bits of dimension 0 (bit set) or exchange the differing lower bits with dimension 0
+    (bit clear); interleave with dimension 0 most significant; Gray-decode."""
+    m = (1 << depth) - 1
+    X = [np.asarray(v).astype(np.int64) & m for v in (x, y, z)]
+    Q = 1 << (depth - 1)
+    while Q > 0:
+        P = Q - 1
+        for d in range(3):
+            on = (X[d] & Q) != 0
+            t = np.where(on, 0, (X[0] ^ X[d]) & P)
+            X[0] = np.where(on, X[0] ^ P, X[0] ^ t)
+            if d != 0:
+                X[d] = X[d] ^ t
+        Q >>= 1
+    g = np.zeros_like(X[0])
+    for i in range(depth):
+        for d in range(3):
+            g |= ((X[d] >> i) & 1) << (3 * i + (2 - d))
+    s = 1
+    while s < 3 * depth:
+        g ^= g >> s
+        s <<= 1
+    return g
+
+
 def encode(grid_coord, batch=None, depth: int = 16, order: str = "z") -> np.ndarray:
     g = np.asarray(grid_coord).astype(np.int64)
     if order == "z":
         code = z_order_key(g[:, 0], g[:, 1], g[:, 2], depth)
     elif order == "z-trans":
         code = z_order_key(g[:, 1], g[:, 0], g[:, 2], depth)
+    elif order == "hilbert":
+        code = hilbert_key(g[:, 0], g[:, 1], g[:, 2], depth)
+    elif order == "hilbert-trans":
+        code = hilbert_key(g[:, 1], g[:, 0], g[:, 2], depth)
     else:
         raise NotImplementedError(order)
     if batch is not None:

@@ -346,7 +346,7 @@ def serialization_fixture():
         coord[1] = 0
         batch = torch.sort(torch.randint(0, nb, (n,), generator=g))[0]
         out[f"{name}.coord"], out[f"{name}.batch"], out[f"{name}.depth"] = coord.numpy(), batch.numpy(), np.int64(depth)
-        for o in ("z", "z-trans"):
+        for o in ("z", "z-trans", "hilbert", "hilbert-trans"):
             out[f"{name}.code.{o}"] = d.encode(coord, batch, depth, order=o).numpy()
         out[f"{name}.code_nobatch.z"] = d.encode(coord, None, depth, order="z").numpy()
     np.savez_compressed(os.path.join(OUT, "serialization.npz"), **out)

@@ -15,7 +15,7 @@ def test_serialization_oracle_matches_reference_golden(name):
     from oracle import serialization_oracle as so
     z = np.load(os.path.join(G, "serialization.npz"))
     coord, batch, depth = z[f"{name}.coord"], z[f"{name}.batch"], int(z[f"{name}.depth"])
-    for o in ("z", "z-trans"):
+    for o in ("z", "z-trans", "hilbert", "hilbert-trans"):
         assert np.array_equal(so.encode(coord, batch, depth, o), z[f"{name}.code.{o}"]), o
     assert np.array_equal(so.encode(coord, None, depth, "z"), z[f"{name}.code_nobatch.z"])
     d, code, order, inverse = so.serialization(coord, batch, ("z", "z-trans"), depth)
@@ -32,7 +32,7 @@ def test_zorder_kernel_bit_exact_vs_reference_golden_and_oracle(name):
     z = np.load(os.path.join(G, "serialization.npz"))
     coord, batch, depth = z[f"{name}.coord"], z[f"{name}.batch"], int(z[f"{name}.depth"])
     c, b = torch.tensor(coord, device="cuda"), torch.tensor(batch, device="cuda")
-    for o in ("z", "z-trans"):
+    for o in ("z", "z-trans", "hilbert", "hilbert-trans"):
         got = ser.encode(c, b, depth, o).cpu().numpy()
         assert np.array_equal(got, z[f"{name}.code.{o}"]), o
     assert np.array_equal(ser.encode(c, None, depth, "z").cpu().numpy(), z[f"{name}.code_nobatch.z"])
@@ -55,7 +55,13 @@ def test_zorder_kernel_large_and_edge_cases():
     assert ser.encode(torch.zeros((0, 3), dtype=torch.int32, device="cuda"), None, 4, "z").numel() == 0
     with pytest.raises(RuntimeError, match="depth"):
         ser.encode(coord[:4].cuda(), None, 17, "z")
-    with pytest.raises(NotImplementedError):
-        ser.encode(coord[:4].cuda(), None, 9, "hilbert")
+    for o in ("hilbert", "hilbert-trans"):
+        got = ser.encode(coord.cuda(), batch.cuda(), 9, o).cpu().numpy()
+        assert np.array_equal(got, so.encode(coord.numpy(), batch.numpy(), 9, o)), o
+        # a Hilbert curve visits face-adjacent cells consecutively: sorted unique cells differ by exactly one step
+    cells = torch.stack(torch.meshgrid(*[torch.arange(8)] * 3, indexing="ij"), -1).reshape(-1, 3).int()
+    hk = ser.encode(cells.cuda(), None, 3, "hilbert").cpu()
+    path = cells[torch.argsort(hk)].long()
+    assert sorted(hk.tolist()) == list(range(512)) and bool(((path[1:] - path[:-1]).abs().sum(1) == 1).all())
     with pytest.raises(RuntimeError, match="CUDA device"):
         ser.encode(coord[:4], None, 9, "z")

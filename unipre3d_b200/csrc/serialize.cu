@@ -34,9 +34,55 @@ zorder_keys_kernel(long long n, int depth, int swap_xy, const int *__restrict__ 
     }
 }
 
+// Hilbert order ("hilbert", and "hilbert-trans" = x and y swapped): Skilling's transpose algorithm exactly as
+// serialization/hilbert.py:96-191 runs it on bit planes -- for every bit from the top, for every dimension: if the bit is
+// set invert the lower bits of dimension 0, else exchange the differing lower bits of dimension 0 and this dimension;
+// then interleave (dimension 0 most significant within a triplet) and Gray-decode the 3*depth-bit word.
+__global__ void __launch_bounds__(256)
+hilbert_keys_kernel(long long n, int depth, int swap_xy, const int *__restrict__ grid_coord, const long long *__restrict__ batch,
+                    long long *__restrict__ code) {
+    const unsigned mask = (1u << depth) - 1u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned X[3] = {(unsigned)grid_coord[3 * i] & mask, (unsigned)grid_coord[3 * i + 1] & mask,
+                         (unsigned)grid_coord[3 * i + 2] & mask};
+        if (swap_xy) { const unsigned t = X[0]; X[0] = X[1]; X[1] = t; }
+        for (unsigned Q = 1u << (depth - 1); Q > 0; Q >>= 1) {
+            const unsigned P = Q - 1;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (X[d] & Q) {
+                    X[0] ^= P;
+                } else {
+                    const unsigned t = (X[0] ^ X[d]) & P;
+                    X[0] ^= t;
+                    X[d] ^= t;
+                }
+            }
+        }
+        unsigned long long g = (part1by2(X[0]) << 2) | (part1by2(X[1]) << 1) | part1by2(X[2]);
+        g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8; g ^= g >> 16; g ^= g >> 32;        // Gray -> binary
+        if (batch) g |= (unsigned long long)batch[i] << (3 * depth);
+        code[i] = (long long)g;
+    }
+}
+
 }  // namespace up3d
 
 using namespace up3d;
+
+extern "C" int up3d_hilbert_keys(int64_t n, int depth, int swap_xy, const int32_t *grid_coord, const int64_t *batch, int64_t *code,
+                                 up3d_stream_t stream) {
+    UP3D_CHECK_ARG(n >= 0, "up3d_hilbert_keys: negative size");
+    UP3D_CHECK_ARG(depth >= 1 && depth <= 16, "up3d_hilbert_keys: depth must be in [1,16] (got %d)", depth);
+    if (n == 0) return 0;
+    UP3D_CHECK_ARG(grid_coord && code, "up3d_hilbert_keys: NULL pointer");
+    const long long blocks = (n + 255) / 256;
+    const int grid = (int)(blocks < (long long)UP3D_NUM_SMS * 16 ? blocks : (long long)UP3D_NUM_SMS * 16);
+    hilbert_keys_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((long long)n, depth, swap_xy, grid_coord, (const long long *)batch,
+                                                               (long long *)code);
+    UP3D_LAUNCH_OK("hilbert_keys_kernel");
+    return 0;
+}
 
 extern "C" int up3d_zorder_keys(int64_t n, int depth, int swap_xy, const int32_t *grid_coord, const int64_t *batch, int64_t *code,
                                 up3d_stream_t stream) {

@@ -3,8 +3,8 @@
 stage of the scene-level PTv3 backbone (SURVEY.md §8a row P1 -- the rest of that row is not built yet).
 
 Keys come from one integer kernel (`up3d_zorder_keys`, csrc/serialize.cu) instead of the reference's 6 table gathers + ORs
-per order; the ordering is a library radix sort (`torch.sort`).  "hilbert" orders are not implemented (the shipped PTv3
-config uses ("z", "z-trans")).
+per order (`up3d_hilbert_keys` for the "hilbert" / "hilbert-trans" orders: Skilling's transpose in registers instead of the
+reference's bit-plane tensors); the ordering is a library radix sort (`torch.sort`).
 """
 from __future__ import annotations
 
@@ -21,15 +21,13 @@ def encode(grid_coord: torch.Tensor, batch: Optional[torch.Tensor] = None, depth
     """grid_coord (n,3) integer voxel coordinates, batch (n) or None -> (n,) int64 keys."""
     if order not in {"z", "z-trans", "hilbert", "hilbert-trans"}:
         raise AssertionError(order)
-    if order.startswith("hilbert"):
-        raise NotImplementedError("hilbert serialization orders are not implemented (PTv3's config uses z / z-trans)")
     require_cuda(grid_coord, batch)
     g = grid_coord.to(torch.int32).contiguous()
     b = None if batch is None else batch.to(torch.int64).contiguous()
     code = torch.empty(g.shape[0], dtype=torch.int64, device=g.device)
     with torch.cuda.device(g.device):
-        check(_lib.lib.up3d_zorder_keys(g.shape[0], int(depth), int(order == "z-trans"), ptr(g), ptr(b), ptr(code), stream_ptr()),
-              launches=1)
+        fn = _lib.lib.up3d_hilbert_keys if order.startswith("hilbert") else _lib.lib.up3d_zorder_keys
+        check(fn(g.shape[0], int(depth), int(order.endswith("-trans")), ptr(g), ptr(b), ptr(code), stream_ptr()), launches=1)
     return code
 
 
