@@ -125,11 +125,24 @@ def main():
     feat = torch.randn(n, 6, generator=g)
     coord = grid_coord.float() * 0.02 + torch.rand(n, 3, generator=g) * 0.01
     data = {"coord": coord.clone(), "grid_coord": grid_coord.clone(), "feat": feat.clone(), "offset": offset.clone()}
+    inter = {}
+    hooks = [net.embedding.register_forward_hook(lambda m, i, o: inter.__setitem__("emb_feat", o.feat.detach().clone())),
+             net.enc.enc0.register_forward_hook(lambda m, i, o: inter.__setitem__("enc0_feat", o.feat.detach().clone())),
+             net.enc.enc1.down.register_forward_hook(lambda m, i, o: inter.__setitem__("down1_feat", o.feat.detach().clone())),
+             net.enc.enc0.block0.cpe.register_forward_hook(lambda m, i, o: inter.__setitem__("cpe0_feat", o.feat.detach().clone())),
+             net.enc.enc0.block0.attn.register_forward_hook(lambda m, i, o: inter.__setitem__("attn0_feat", o.feat.detach().clone()))]
+    # SerializedPooling is built with its default shuffle_orders=True (the model-level flag is not forwarded to it,
+    # point_transformer_v3m1_base.py:633-641): every forward draws torch.randperm(2) per pooling layer from the global CPU
+    # generator.  Seed it so that the consumer of this fixture can replay the same draws.
+    torch.manual_seed(1234)
     with torch.no_grad():
         point = net(data, None, None, None)
+    for h in hooks:
+        h.remove()
     out = {"cfg_json": np.array(repr(kw)), "coord": coord.numpy(), "grid_coord": grid_coord.numpy(), "feat": feat.numpy(),
            "offset": offset.numpy(), "out_feat": point.feat.numpy(), "out_coord": point.coord.numpy(),
            "out_batch": point.batch.numpy()}
+    out.update({"inter." + k: v.numpy() for k, v in inter.items()})
     out.update({"sd." + k: v.numpy() for k, v in net.state_dict().items()})
     np.savez_compressed(os.path.join(OUT, "ptv3_small.npz"), **out)
     print("wrote ptv3_small.npz", point.feat.shape, float(point.feat.abs().max()))

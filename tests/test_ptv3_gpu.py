@@ -28,10 +28,36 @@ def _net_and_data():
     return net.cuda().train(), data, z
 
 
+def test_keep_order_sparse_tensor_equals_sorted_one():
+    """PTv3's row-aligned sparse tensor (keep_order=True) gives the same convolution as the sorted layout."""
+    from unipre3d_b200.sparse import SparseConvTensor, SubMConv3d
+    g = torch.Generator().manual_seed(0)
+    cells = torch.randperm(10 ** 3, generator=g)[:400]
+    idx = torch.stack([cells * 0, cells // 100, (cells // 10) % 10, cells % 10], 1).int().cuda()
+    feat = torch.randn(400, 32, generator=g).cuda()
+    conv = SubMConv3d(32, 48, 3, bias=True, indice_key="k").cuda()
+    a = conv(SparseConvTensor(feat, idx, keep_order=True))
+    b = conv(SparseConvTensor(feat, idx))
+    assert torch.equal(a.indices, idx) and torch.allclose(a.features, b.features_in_input_order(), atol=1e-6)
+
+
 def test_ptv3_forward_matches_reference_fixture():
     net, data, z = _net_and_data()
+    inter = {}
+    hooks = [net.embedding.register_forward_hook(lambda m, i, o: inter.__setitem__("emb_feat", o.feat.detach().clone())),
+             net.enc.enc0.block0.cpe.register_forward_hook(lambda m, i, o: inter.__setitem__("cpe0_feat", o.feat.detach().clone())),
+             net.enc.enc0.block0.attn.register_forward_hook(lambda m, i, o: inter.__setitem__("attn0_feat", o.feat.detach().clone())),
+             net.enc.enc0.register_forward_hook(lambda m, i, o: inter.__setitem__("enc0_feat", o.feat.detach().clone())),
+             net.enc.enc1.down.register_forward_hook(lambda m, i, o: inter.__setitem__("down1_feat", o.feat.detach().clone()))]
+    torch.manual_seed(1234)          # the pooling layers' torch.randperm order shuffles (see make_golden_ptv3.py)
     with torch.no_grad():
         point = net(data)
+    for h in hooks:
+        h.remove()
+    for k in ("emb_feat", "cpe0_feat", "attn0_feat", "enc0_feat", "down1_feat"):      # stage by stage, to localise a mismatch
+        ref = z["inter." + k]
+        e = np.abs(inter[k].cpu().numpy() - ref).max()
+        assert e <= 2e-2 * np.abs(ref).max(), (k, e, np.abs(ref).max())
     assert point.feat.shape == z["out_feat"].shape
     assert np.array_equal(point.batch.cpu().numpy(), z["out_batch"])
     np.testing.assert_allclose(point.coord.cpu().numpy(), z["out_coord"], atol=1e-6)
@@ -47,6 +73,7 @@ def test_ptv3_trains_and_flash_branch_is_close():
         if m.__class__.__name__ == "SerializedAttention":
             del m.attn_drop                                    # nn.Dropout in the exact branch, a float in the fused one
             m.enable_flash, m.patch_size, m.attn_drop = True, m.patch_size_max, 0.0
+    torch.manual_seed(1234)
     with torch.no_grad():
         fast = net({k: v.clone() for k, v in data.items()}).feat
     assert float((fast - ref).abs().max()) <= 0.1 * float(ref.abs().max())
