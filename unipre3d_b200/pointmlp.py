@@ -36,6 +36,9 @@ def get_activation(activation):
     return table[a]() if a in table else nn.ReLU(inplace=True)
 
 
+PREFETCH_GEOMETRY = True      # tests flip it to compare against the in-line order of the reference
+
+
 def _pw(conv: nn.Conv1d, rows: torch.Tensor) -> torch.Tensor:
     """Conv1d(kernel 1, groups 1) on channels-last rows."""
     return F.linear(rows, conv.weight.squeeze(-1), conv.bias)
@@ -69,15 +72,22 @@ class LocalGrouper(nn.Module):
             self.affine_alpha = nn.Parameter(torch.ones([1, 1, 1, channel + add_channel]))
             self.affine_beta = nn.Parameter(torch.zeros([1, 1, 1, channel + add_channel]))
 
-    def forward(self, xyz, points):
-        """xyz (B,N,C), points (B,N,d) -> new_xyz (B,S,C), new_points (B,S,k,2d[+..])"""
+    def geometry(self, xyz):
+        """The part of forward() that depends on the coordinates only: (fps_idx, new_xyz, knn idx)."""
         B, N, C = xyz.shape
         S = N // self.sample_ratio
         xyz = xyz.contiguous()
         fps_idx = _fps_like_reference(xyz, S).long()
         new_xyz = index_points(xyz, fps_idx)
+        return fps_idx, new_xyz, pointops.knn_point(self.kneighbors, xyz, new_xyz)
+
+    def forward(self, xyz, points, geom=None):
+        """xyz (B,N,C), points (B,N,d) -> new_xyz (B,S,C), new_points (B,S,k,2d[+..]); `geom` = a prefetched geometry()"""
+        B, N, C = xyz.shape
+        S = N // self.sample_ratio
+        xyz = xyz.contiguous()
+        fps_idx, new_xyz, idx = geom if geom is not None else self.geometry(xyz)
         new_points = index_points(points, fps_idx)
-        idx = pointops.knn_point(self.kneighbors, xyz, new_xyz)
         grouped_points = index_points(points, idx)                                  # (B,S,k,d)
         if self.use_xyz:
             grouped_points = torch.cat([grouped_points, index_points(xyz, idx)], dim=-1)
@@ -163,7 +173,7 @@ class PointNetFeaturePropagation(nn.Module):
                                             activation=activation)
         self.has_MLP = has_MLP
 
-    def forward(self, xyz1, xyz2, points1, points2):
+    def forward(self, xyz1, xyz2, points1, points2, nn3=None):
         """xyz1 (B,N,C) dense, xyz2 (B,S,C) sparse, points1 (B,N,D') or None, points2 (B,S,D'') -> (B,N,D''')
         (all channels-last).  3-NN inverse-distance interpolation, pointmlp.py:397-409."""
         B, N, _ = xyz1.shape
@@ -171,7 +181,8 @@ class PointNetFeaturePropagation(nn.Module):
         if S == 1:
             interpolated = points2.expand(-1, N, -1)
         else:
-            idx, dists = pointops.knn_point(3, xyz2, xyz1, return_dist=True)        # (B,N,3)
+            # nn3: prefetched knn_point(3, xyz2, xyz1, return_dist=True)
+            idx, dists = nn3 if nn3 is not None else pointops.knn_point(3, xyz2, xyz1, return_dist=True)   # (B,N,3)
             dist_recip = 1.0 / (dists + 1e-8)
             weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
             interpolated = torch.sum(index_points(points2, idx) * weight.view(B, N, 3, 1).to(points2.dtype), dim=2)
@@ -229,19 +240,53 @@ class PointMLPEncoder(nn.Module):
             p, x = p["pos"], p.get("x", None)
         b, n, c = p.shape
         rows = p.reshape(b * n, c) if x is None else x.transpose(1, 2).reshape(b * n, -1)
+        # Everything that depends on the coordinates only -- the four sequential farthest-point samplings (4095 + 2047 +
+        # 1023 + 511 dependent rounds: ~5 ms of a 37 ms step), the kNN tables and the decoder's 3-NN tables -- is issued
+        # on a side stream now and joined stage by stage, so it overlaps the Conv-BN-ReLU blocks of the earlier stages.
+        geoms, nn3s, ready = [None] * self.stages, [None] * len(self.decode_list), None
+        if p.is_cuda and PREFETCH_GEOMETRY:
+            from .fused_encoder import _SIDE_STREAMS
+            main = torch.cuda.current_stream(p.device)
+            key = ("pmlp", p.device.index if p.device.index is not None else torch.cuda.current_device())
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=p.device)
+            side = _SIDE_STREAMS[key]
+            side.wait_stream(main)
+            ready = []
+            with torch.cuda.stream(side), torch.no_grad():
+                q, pts = p, [p]
+                for i in range(self.stages):
+                    geoms[i] = self.local_grouper_list[i].geometry(q)
+                    q = geoms[i][1]
+                    pts.append(q)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    ready.append(ev)
+                rev = list(reversed(pts))
+                for i in range(len(self.decode_list)):
+                    if rev[i].shape[1] > 1:
+                        nn3s[i] = pointops.knn_point(3, rev[i], rev[i + 1], return_dist=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                ready.append(ev)
+            p.record_stream(side)
         x = self.embedding(rows).reshape(b, n, -1)                                  # (B,N,D) channels-last
         p_list, x_list = [p], [x]
         for i in range(self.stages):
-            p, g = self.local_grouper_list[i](p, x)
+            if ready is not None:
+                torch.cuda.current_stream(p.device).wait_event(ready[i])
+            p, g = self.local_grouper_list[i](p, x, geoms[i])
             x = self.pos_blocks_list[i](self.pre_blocks_list[i](g))
             p_list.append(p)
             x_list.append(x)
+        if ready is not None:
+            torch.cuda.current_stream(p.device).wait_event(ready[-1])
         p_list.reverse()
         x_list.reverse()
         x = x_list[0]
         last = len(self.decode_list) - 1
         for i in range(len(self.decode_list)):
-            x = self.decode_list[i](p_list[i + 1], p_list[i], x_list[i + 1], x)
+            x = self.decode_list[i](p_list[i + 1], p_list[i], x_list[i + 1], x, nn3s[i])
             if self.use_fusion and feature_mlps is not None and i == last:
                 x = FeatureFusion(feature_mlps)(x, p_list[i + 1][..., :3], image_features, c2w_projection_matrix,
                                                 intrinsic)
