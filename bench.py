@@ -385,6 +385,49 @@ def legacy_gpu_pointops(device, reps: int = 20):
     return out
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank: int, world: int):
+    """Pin this process (and, by first touch, its pinned staging buffers) to the host cores that are local to its GPU
+    (/sys/bus/pci/devices/<gpu>/local_cpulist).  Without it the step's host->device copy may cross the socket
+    interconnect: on this pool the same 8.66 MB copy took 0.3 ms or 4-5 ms depending on where the process happened to
+    run.  Ranks that share a NUMA node split its cores.  UP3D_NO_NUMA_BIND=1 disables it."""
+    if os.environ.get("UP3D_NO_NUMA_BIND"):
+        return "disabled"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(vis[local_rank]) if local_rank < len(vis) else local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            cpus = sorted(_parse_cpulist(f.read()))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return "no local cpus"
+        if world > 1:                                        # ranks on the same node: disjoint slices of its cores
+            per = max(1, len(allowed) // max(1, min(world, 4)))
+            k = local_rank % max(1, len(allowed) // per)
+            allowed = allowed[k * per:(k + 1) * per] or allowed
+        os.sched_setaffinity(0, set(allowed))
+        torch.set_num_threads(min(len(allowed), 8))
+        return f"{len(allowed)} cores local to {bus}"
+    except Exception as e:                                   # never fail the bench because of a missing sysfs file
+        return f"unavailable ({type(e).__name__})"
+
+
 def ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -392,18 +435,10 @@ def ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
+    binding = bind_to_gpu_numa_node(local, world)          # before the CUDA context and any pinned allocation
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # one slice of the host cores per rank (all ranks otherwise pile onto NUMA node 0's cores and the end-to-end
-        # path -- pinned-memory copies, launch threads -- contends)
-        try:
-            ncpu = os.cpu_count() or 1
-            per = max(1, ncpu // world)
-            os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
-            torch.set_num_threads(min(per, 8))
-        except Exception:
-            pass
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
@@ -556,7 +591,7 @@ def ours(args):
                                        f"256x256, {GAUSSIANS_PER_OBJECT} Gaussians/object, SH degree 1 (BASELINE.json "
                                        + ("configs[1])" if CFG_NAME.startswith("transformer") else "configs[2], per-GPU share)"),
                            "objects_per_gpu": OBJECTS_PER_GPU, "views_per_step": views_per_step, "parallelism": f"dp{n_gpus}",
-                           "cuda_graph": bool(use_graph),
+                           "cuda_graph": bool(use_graph), "host_binding": binding,
                            "host_images": ("float32 (divided by 255 on the host, as the reference loader)" if args.float_images
                                            else "uint8 as decoded from the dataset's PNGs; /255 on the device"),
                            "l2": "256 MiB buffer written between timed iterations (L2 flush), per-step CUDA-event pairs"},
