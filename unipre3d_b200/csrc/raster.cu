@@ -506,6 +506,171 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) depth_sort_kernel(const SortA
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2a'. the same sort for LARGE sets (> SORT_SMEM_MAX_KEYS Gaussians per view: scene level, 10^5 keys): one thread-block
+// CLUSTER of SORT_CLUSTER CTAs per view instead of one CTA.  CTA c owns the c-th contiguous slice of the view's keys; per
+// 8-bit pass every CTA histograms its slice, the 256-bin histograms are exchanged through distributed shared memory
+// (digit d of CTA c starts at  sum_{d' < d} total[d'] + sum_{c' < c} hist[c'][d]  -- a stable LSD radix sort across CTAs),
+// and each CTA scatters its slice.  Keys / ids ping-pong in the (L2-resident) global scratch.  Two cluster barriers per
+// pass.  Same order as the single-CTA kernel, bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int SORT_CLUSTER = 8;
+
+__device__ __forceinline__ uint32_t sort_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void sort_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t sort_dsmem_ld(const uint32_t *local, uint32_t rank) {
+    uint32_t remote, v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+__global__ void __cluster_dims__(SORT_CLUSTER, 1, 1) __launch_bounds__(SORT_THREADS, 1)
+depth_sort_cluster_kernel(const SortArgs a) {
+    __shared__ uint32_t wcnt[SORT_WARPS * 256];
+    __shared__ uint32_t hist[256];          // this CTA's slice histogram (read remotely by the peers)
+    __shared__ uint32_t dbase[256];
+    __shared__ uint32_t tot[256];
+    __shared__ uint32_t misc[SORT_MISC];
+    __shared__ uint32_t s_valid;            // un-culled keys of this CTA's slice (read remotely)
+    const int v = blockIdx.x / SORT_CLUSTER;
+    const int c = (int)sort_cluster_rank();
+    const int rec0 = a.view_rec_start[v];
+    const int n = a.view_rec_start[v + 1] - rec0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = ((n + SORT_CLUSTER - 1) / SORT_CLUSTER + 31) & ~31;
+    const int s0 = min(n, c * per), s1 = min(n, s0 + per);
+
+    uint32_t *kA = a.sc.kA + rec0, *kB = a.sc.kB + rec0;
+    int32_t *iA = a.sc.iA + rec0, *iB = a.sc.iB + rec0;
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
+    int my_valid = 0;
+    for (int i = s0 + tid; i < s1; i += SORT_THREADS) {
+        const uint32_t k = a.st.key[rec0 + i];
+        kA[i] = k;
+        iA[i] = i;
+        my_valid += (k != KEY_CULLED);
+    }
+    my_valid = __reduce_add_sync(0xffffffffu, my_valid);
+    if (lane == 0 && my_valid) atomicAdd(&s_valid, (uint32_t)my_valid);
+    __syncthreads();
+    sort_cluster_sync();
+    int n_vis = 0;
+    for (int cc = 0; cc < SORT_CLUSTER; ++cc) n_vis += (int)sort_dsmem_ld(&s_valid, (uint32_t)cc);
+    if (c == 0 && tid == 0) a.st.n_vis[v] = n_vis;
+
+    for (int shift = 0; shift < 32; shift += 8) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int base = s0; base < s1; base += SORT_THREADS) {
+            const int i = base + tid;
+            const uint32_t dgt = (i < s1) ? ((kA[i] >> shift) & 0xFFu) : 0xFFFFu;
+            const unsigned peers = __match_any_sync(0xffffffffu, dgt);
+            if (dgt != 0xFFFFu && lane == (__ffs(peers) - 1)) atomicAdd(&hist[dgt], (uint32_t)__popc(peers));
+        }
+        __syncthreads();
+        sort_cluster_sync();                              // every slice histogram is complete and visible
+        uint32_t before = 0, total = 0;
+        if (tid < 256) {
+            for (int cc = 0; cc < SORT_CLUSTER; ++cc) {
+                const uint32_t h = sort_dsmem_ld(&hist[tid], (uint32_t)cc);
+                total += h;
+                before += (cc < c) ? h : 0u;
+            }
+            tot[tid] = total;
+        }
+        const int same = __syncthreads_or(tid < 256 && total == (uint32_t)n);     // identical in every CTA of the cluster
+        if (!same) {
+            if (tid < 256) {                              // exclusive scan of the 256 totals (as the single-CTA kernel)
+                uint32_t x = tot[tid], incl = x;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                dbase[tid] = incl - x + before;
+                if (lane == 31) misc[1 + warp] = incl;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t add = 0;
+                for (int w = 0; w < warp; ++w) add += misc[1 + w];
+                dbase[tid] += add;
+            }
+            __syncthreads();
+            for (int tile0 = s0; tile0 < s1; tile0 += SORT_TILE) {
+                for (int j = tid; j < SORT_WARPS * 256; j += SORT_THREADS) wcnt[j] = 0;
+                __syncthreads();
+                uint32_t keys[SORT_RPW];
+                int32_t ids[SORT_RPW];
+                uint32_t rank[SORT_RPW];
+                uint32_t *mycnt = wcnt + warp * 256;
+#pragma unroll
+                for (int r = 0; r < SORT_RPW; ++r) {
+                    const int i = tile0 + (warp * SORT_RPW + r) * 32 + lane;
+                    const bool valid = i < s1;
+                    keys[r] = valid ? kA[i] : 0u;
+                    ids[r] = valid ? iA[i] : 0;
+                    const uint32_t dgt = valid ? ((keys[r] >> shift) & 0xFFu) : 0xFFFFu;
+                    const unsigned peers = __match_any_sync(0xffffffffu, dgt);
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t old = 0;
+                    if (valid && lane == leader) {
+                        old = mycnt[dgt];
+                        mycnt[dgt] = old + (uint32_t)__popc(peers);
+                    }
+                    old = __shfl_sync(0xffffffffu, old, leader);
+                    rank[r] = old + (uint32_t)__popc(peers & lanemask_lt());
+                    __syncwarp();
+                }
+                __syncthreads();
+                if (tid < 256) {
+                    uint32_t run = dbase[tid];
+                    for (int w = 0; w < SORT_WARPS; ++w) {
+                        const uint32_t cnt = wcnt[w * 256 + tid];
+                        wcnt[w * 256 + tid] = run;
+                        run += cnt;
+                    }
+                    dbase[tid] = run;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < SORT_RPW; ++r) {
+                    const int i = tile0 + (warp * SORT_RPW + r) * 32 + lane;
+                    if (i < s1) {
+                        const uint32_t pos = mycnt[(keys[r] >> shift) & 0xFFu] + rank[r];
+                        kB[pos] = keys[r];
+                        iB[pos] = ids[r];
+                    }
+                }
+                __syncthreads();
+            }
+            uint32_t *tk = kA; kA = kB; kB = tk;
+            int32_t *ti = iA; iA = iB; iB = ti;
+            __threadfence();
+        }
+        sort_cluster_sync();                              // scatter visible cluster-wide; remote histogram reads are done
+    }
+    // re-layout: each CTA gathers its slice of the sorted order
+    for (int k = s0 + tid; k < min(s1, n_vis); k += SORT_THREADS) {
+        const int id = iA[k];
+        const int src = rec0 + id, dst = rec0 + k;
+        a.st.s_id[dst] = id;
+        a.st.s_xy[dst] = a.st.u_xy[src];
+        a.st.s_co[dst] = a.st.u_co[src];
+        a.st.s_rgb[dst] = a.st.u_rgb[src];
+        a.st.s_rect[dst] = a.st.u_rect[src];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2b. coarse bins (small-footprint views only)
 //
 // In the reference's object regime every Gaussian covers every tile and a tile's list IS the view's depth order, so the
@@ -1373,7 +1538,11 @@ int up3d_raster_forward(const up3d_raster_desc *d, const float *means3D, const f
     if (sa.use_smem) sort_smem += (size_t)((d->max_set_size + 3) & ~3) * 16;
     if (ensure_dyn_smem((const void *)depth_sort_kernel, g_sort_smem, sort_smem)) return 1;
     tick(1, stream);
-    {
+    if (!sa.use_smem) {
+        // large sets: a cluster of SORT_CLUSTER CTAs per view (keys ping-pong in the global scratch)
+        depth_sort_cluster_kernel<<<V * SORT_CLUSTER, SORT_THREADS, 0, stream>>>(sa);
+        UP3D_LAUNCH_OK("depth_sort_cluster_kernel");
+    } else {
         const size_t smem = sort_smem;
         depth_sort_kernel<<<V, SORT_THREADS, smem, stream>>>(sa);
         UP3D_LAUNCH_OK("depth_sort_kernel");
