@@ -189,12 +189,31 @@ class ImageFeaturePredictor(nn.Module):
         self.encoder = AutoencoderKL()
         if pretrained_path is not None:
             sd = torch.load(pretrained_path, map_location="cpu")
-            self.encoder.load_state_dict(sd.get("model", sd) if isinstance(sd, dict) else sd, strict=True)
+            sd = sd.get("model", sd) if isinstance(sd, dict) else sd
+            self.encoder.load_state_dict(self.remap_legacy_attention_keys(sd), strict=True)
         self.encoder.eval()
         for p in self.encoder.parameters():
             p.requires_grad = False
         self.encoder_config = self.encoder.config
-        self.compute_dtype = torch.bfloat16        # frozen, no gradient: bf16 tensor-core convolutions on CUDA
+        # None: follow the caller -- fp32 unless a torch.autocast region is active (the reference runs the VAE in fp32,
+        # its config sets force_upcast); a dtype here forces that autocast dtype on CUDA
+        self.compute_dtype = None
+
+    @staticmethod
+    def remap_legacy_attention_keys(sd):
+        """Older sd-vae checkpoints name the mid-block attention projections query / key / value / proj_attn; diffusers
+        remaps them to to_q / to_k / to_v / to_out.0 on load (and reshapes their 1x1-conv weights to Linear).  Same here,
+        so that such a file loads strictly.  (Untested against the real file: no weights are shipped or downloadable.)"""
+        ren = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
+        out = {}
+        for k, v in sd.items():
+            parts = k.split(".")
+            if "attentions" in parts and len(parts) >= 2 and parts[-2] in ren:
+                parts[-2:-1] = ren[parts[-2]].split(".")
+                if v.ndim == 4 and parts[-1] == "weight":
+                    v = v.reshape(v.shape[0], v.shape[1])
+            out[".".join(parts)] = v
+        return out
 
     def train(self, mode: bool = True):
         super().train(mode)
@@ -205,7 +224,10 @@ class ImageFeaturePredictor(nn.Module):
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         feats: Dict[str, torch.Tensor] = {}
         if x.is_cuda:
-            with torch.autocast("cuda", dtype=self.compute_dtype):
+            dt = self.compute_dtype
+            if dt is None and torch.is_autocast_enabled("cuda"):
+                dt = torch.get_autocast_dtype("cuda")
+            with torch.autocast("cuda", dtype=dt or torch.bfloat16, enabled=dt is not None):
                 self.encoder(x.contiguous(memory_format=torch.channels_last), collect=feats, stop_after=3)
             return {k: v.float() for k, v in feats.items()}
         self.encoder(x.float(), collect=feats, stop_after=3)

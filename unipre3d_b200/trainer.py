@@ -551,6 +551,10 @@ class Trainer:
                 self._stage(prefetch)
             self._graph.replay()
             loss = self._loss_buf
+        # NB (differs from the reference on a NaN/Inf step): the reference `continue`s before scheduler.step() and
+        # ema.update() (train_network.py:336-352); here the skip decision lives on the device (found_inf inside the fused
+        # optimizer, no host sync), so the StepLR counter and the EMA schedule advance on a skipped step as well.  The
+        # parameters, moments and Adam step counter are untouched on such a step, as in the reference.
         mm.scheduler_step()
         if mm.ema:
             mm.ema.update()
