@@ -615,19 +615,90 @@ def ours(args):
         os._exit(0)
 
 
+SCENE_CONFIGS = {
+    # BASELINE.json configs[3]: ptv3_pretraining (ScanNet-shaped scene), 100k points, 4 views 512x512 -- per-GPU share: 1 scene
+    "ptv3": dict(name="ptv3_pretraining", points=100_000, views=4, sh=1),
+    # configs[4]: sparseunet_pretraining scene, 200k points, 8 views 512x512, SH degree 3 (stress) -- per-GPU share: 1 scene
+    "sparseunet": dict(name="sparseunet_pretraining", points=200_000, views=8, sh=3),
+}
+
+
+def ours_scene(args):
+    """Scene-level configs (eager step: voxel counts are data dependent, no CUDA graph): one scene per GPU, backbone on
+    the sparse-convolution engine -> per-scene Gaussian list -> all views in one binned raster call -> L2 -> backward ->
+    fused clip + AdamW.  `opt.use_fusion=false` (PointFusion is not built)."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device")
+    sc = SCENE_CONFIGS[args.config]
+    binding = bind_to_gpu_numa_node(0, 1)
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    from unipre3d_b200 import _lib, synthetic
+    from unipre3d_b200.config import compose
+    from unipre3d_b200.trainer import Trainer, _to_device
+    cfg = compose(sc["name"], overrides=["opt.use_fusion=false", "data.input_images=0", f"opt.imgs_per_obj={sc['views']}",
+                                         "data.training_width=512", "data.training_height=512", "opt.batch_size=1",
+                                         f"model.max_sh_degree={sc['sh']}", "opt.ema.use=false"])
+    trainer = Trainer(cfg, device=device, use_cuda_graph=False)
+    batches = [synthetic.make_scene_batch(cfg, 1, sc["points"], seed=i) for i in range(2)]
+    n_vox = int(batches[0]["point_cloud"]["coord"].shape[0])
+    for i in range(max(args.warmup, 3)):
+        trainer.train_iteration(batches[i % 2])
+    torch.cuda.synchronize()
+    resident = _to_device(batches[0], device, non_blocking=False)
+    steps = args.steps
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def timed(fn):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for i in range(steps):
+            flush.zero_()
+            ev[i][0].record()
+            fn(i)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev) / steps
+
+    before = _lib.launch_count
+    with ClockSampler(0) as clk:
+        ms = timed(lambda i: trainer._step_body(resident))
+        ms_e2e = timed(lambda i: trainer.train_iteration(batches[i % 2]))
+    launches = _lib.launch_count - before
+    h2d = sum(t.numel() * t.element_size() for _, t in __import__("unipre3d_b200.trainer", fromlist=["_flat_items"])._flat_items(batches[0]))
+    V = sc["views"]
+    line = {"metric": "views/sec, full pre-training step (scene level)", "value": V / (ms * 1e-3), "unit": "views/s", "n_gpus": 1,
+            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 features / rasterizer / optimizer; sparse-conv operands bf16 (fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": f"{sc['name']} (opt.use_fusion=false): 1 scene per GPU, {sc['points']} surface points -> {n_vox} "
+                                   f"voxels at 0.02 m = Gaussians, {V} views 512x512, SH degree {sc['sh']} (BASELINE.json "
+                                   f"configs[{3 if args.config == 'ptv3' else 4}], per-GPU share)",
+                       "cuda_graph": False, "host_binding": binding,
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush), per-step CUDA-event pairs"},
+            "clocks": clk.summary(),
+            "e2e": {"value": V / (ms_e2e * 1e-3), "unit": "views/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="transformer", choices=["transformer", "pointmlp"],
-                    help="transformer = BASELINE configs[1] (headline); pointmlp = configs[2] per-GPU share (4 objects)")
+    ap.add_argument("--config", default="transformer", choices=["transformer", "pointmlp", "ptv3", "sparseunet"],
+                    help="transformer = BASELINE configs[1] (headline); pointmlp = configs[2] per-GPU share (4 objects); "
+                         "ptv3 / sparseunet = configs[3] / [4] per-GPU share (1 scene, eager step)")
     ap.add_argument("--fp32", action="store_true", help="keep the backbone GEMMs in fp32 (reference precision)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--float-images", action="store_true", help="host batches carry float32 images (4x the H2D bytes)")
     args = ap.parse_args()
+    if args.config in SCENE_CONFIGS and args.impl == "ours":
+        return ours_scene(args)
     select_config(args.config)
     if args.impl == "reference":
         reference_arm(args)

@@ -159,11 +159,11 @@ class PointFeaturePredictor(nn.Module):
         elif model_type == "sparseunet":
             from .sparse_unet import SpUNetBase
             self.encoder = SpUNetBase(in_channels=6, num_classes=64, cfg=cfg)          # point_predictor.py:64-67
-            self.final = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 23))
+            self.final = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, self._head_width(out_channels)))
         elif model_type == "ptv3":
             from .ptv3 import PointTransformerV3
             self.encoder = PointTransformerV3(in_channels=6, cfg=cfg)                   # point_predictor.py:68-69
-            self.final = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 23))
+            self.final = nn.Sequential(nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, self._head_width(out_channels)))
         else:
             raise NotImplementedError(
                 f"backbone_type={model_type!r}: 'transformer' (SURVEY.md §8a rows B1-B5), 'pointmlp' (row B6), 'sparseunet' "
@@ -173,6 +173,12 @@ class PointFeaturePredictor(nn.Module):
             print(f"Loaded pretrained weights from {pretrained_path}")
             print(f"Missing keys: {info.missing_keys}")
             print(f"Unexpected keys: {info.unexpected_keys}")
+
+    @staticmethod
+    def _head_width(split_dimensions) -> int:
+        """The reference hard-codes 23 output channels (SH degree 1, point_predictor.py:77-80); other degrees -- the SH
+        degree 3 stress configuration of BASELINE.json configs[4] -- need sum(split_dimensions)."""
+        return int(sum(split_dimensions))
 
     def forward(self, x):
         x, center = self.encoder(x, None, None, None, None)
