@@ -639,7 +639,8 @@ def ours_scene(args):
     cfg = compose(sc["name"], overrides=["opt.use_fusion=false", "data.input_images=0", f"opt.imgs_per_obj={sc['views']}",
                                          "data.training_width=512", "data.training_height=512", "opt.batch_size=1",
                                          f"model.max_sh_degree={sc['sh']}", "opt.ema.use=false"])
-    trainer = Trainer(cfg, device=device, use_cuda_graph=False)
+    autocast = None if args.fp32 else torch.bfloat16      # dense Linear / attention layers of PTv3 and the heads
+    trainer = Trainer(cfg, device=device, use_cuda_graph=False, autocast_dtype=autocast)
     batches = [synthetic.make_scene_batch(cfg, 1, sc["points"], seed=i) for i in range(2)]
     n_vox = int(batches[0]["point_cloud"]["coord"].shape[0])
     for i in range(max(args.warmup, 3)):
@@ -669,7 +670,9 @@ def ours_scene(args):
     V = sc["views"]
     line = {"metric": "views/sec, full pre-training step (scene level)", "value": V / (ms * 1e-3), "unit": "views/s", "n_gpus": 1,
             "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 features / rasterizer / optimizer; sparse-conv operands bf16 (fp32 accumulate)",
+            "vs_baseline": None,
+            "dtype": "f32 features / rasterizer / optimizer; sparse-conv operands bf16 (fp32 accumulate); dense Linear / attention "
+                     + ("f32" if args.fp32 else "bf16 autocast"),
             "data": "synthetic",
             "config": {"workload": f"{sc['name']} (opt.use_fusion=false): 1 scene per GPU, {sc['points']} surface points -> {n_vox} "
                                    f"voxels at 0.02 m = Gaussians, {V} views 512x512, SH degree {sc['sh']} (BASELINE.json "

@@ -65,14 +65,26 @@ __global__ void __launch_bounds__(256) subm_rulebook_kernel(int n, int K, const 
 }
 
 // ------------------------------------------------------------------------------------------------ forward / dX
-// grid (ceil(n_out / 64), C_out / (16 * NT)); NT = 16-column accumulator fragments per warp
+// grid (ceil(n_out / 64), C_out / (16 * NT)); NT = 16-column accumulator fragments per warp.
+// Per kernel offset and per 64-channel K chunk: the weight slice W[o][k0:k0+64, col0:col0+16 NT] is copied to shared
+// memory with cp.async (coalesced 16-byte pieces, in flight while the input rows are gathered), the 64 gathered input rows
+// are converted fp32 -> bf16 into shared memory, then both MMA operands come from shared memory.  (The first version read
+// the B fragments straight from global memory: 36 dependent L2 round trips per offset made it 3.5x slower.)
+constexpr int KC = 64;            // K chunk (input channels per staging round)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
+
 template <int NT>
 __global__ void __launch_bounds__(THREADS)
 conv_kernel(int n_out, int Cin, int Cout, int KV, const int *__restrict__ nbr, const float *__restrict__ in,
             const bf16 *__restrict__ w, float *__restrict__ out) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    bf16 *As = reinterpret_cast<bf16 *>(smem_raw);                 // [ROWS][Cin + PAD]
-    const int lda = Cin + PAD;
+    constexpr int LDA = KC + PAD, LDB = 16 * NT + PAD;
+    bf16 *As = reinterpret_cast<bf16 *>(smem_raw);                 // [ROWS][LDA]
+    bf16 *Bs = As + ROWS * LDA;                                    // [KC][LDB]
     __shared__ int s_idx[ROWS];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row0 = blockIdx.x * ROWS, col0 = blockIdx.y * (16 * NT);
@@ -81,7 +93,6 @@ conv_kernel(int n_out, int Cin, int Cout, int KV, const int *__restrict__ nbr, c
 #pragma unroll
     for (int j = 0; j < NT; ++j) wmma::fill_fragment(acc[j], 0.f);
 
-    const int c4n = Cin / 4;                                       // float4 chunks per row
     for (int o = 0; o < KV; ++o) {
         int my = -1;
         if (tid < ROWS) {
@@ -91,30 +102,41 @@ conv_kernel(int n_out, int Cin, int Cout, int KV, const int *__restrict__ nbr, c
         }
         // offsets that no row of this tile uses cost one barrier and no memory traffic
         if (!__syncthreads_or(my >= 0)) continue;
-        for (int e = tid; e < ROWS * c4n; e += THREADS) {
-            const int r = e / c4n, c4 = e % c4n;
-            const int src = s_idx[r];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (src >= 0) v = *reinterpret_cast<const float4 *>(in + (size_t)src * Cin + 4 * c4);
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const unsigned *>(&lo);
-            pk.y = *reinterpret_cast<const unsigned *>(&hi);
-            *reinterpret_cast<uint2 *>(As + r * lda + 4 * c4) = pk;
-        }
-        __syncthreads();
-        const bf16 *wo = w + (size_t)o * Cin * Cout + col0;
-        for (int kc = 0; kc < Cin; kc += 16) {
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> af;
-            wmma::load_matrix_sync(af, As + (warp * 16) * lda + kc, lda);
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> bfr;
-                wmma::load_matrix_sync(bfr, wo + (size_t)kc * Cout + 16 * j, Cout);
-                wmma::mma_sync(acc[j], af, bfr, acc[j]);
+        for (int k0 = 0; k0 < Cin; k0 += KC) {
+            const int kw = min(KC, Cin - k0);                      // multiple of 16
+            // B slice: kw rows x 16 NT columns, 2 NT 16-byte pieces per row
+            const bf16 *wsrc = w + ((size_t)o * Cin + k0) * Cout + col0;
+            for (int e = tid; e < kw * (2 * NT); e += THREADS) {
+                const int r = e / (2 * NT), p8 = e % (2 * NT);
+                cp_async16(Bs + r * LDB + 8 * p8, wsrc + (size_t)r * Cout + 8 * p8);
             }
+            // A chunk: gathered rows, fp32 -> bf16
+            const int c4n = kw / 4;
+            for (int e = tid; e < ROWS * c4n; e += THREADS) {
+                const int r = e / c4n, c4 = e % c4n;
+                const int src = s_idx[r];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src >= 0) v = *reinterpret_cast<const float4 *>(in + (size_t)src * Cin + k0 + 4 * c4);
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const unsigned *>(&lo);
+                pk.y = *reinterpret_cast<const unsigned *>(&hi);
+                *reinterpret_cast<uint2 *>(As + r * LDA + 4 * c4) = pk;
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            for (int kc = 0; kc < kw; kc += 16) {
+                wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> af;
+                wmma::load_matrix_sync(af, As + (warp * 16) * LDA + kc, LDA);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> bfr;
+                    wmma::load_matrix_sync(bfr, Bs + kc * LDB + 16 * j, LDB);
+                    wmma::mma_sync(acc[j], af, bfr, acc[j]);
+                }
+            }
+            __syncthreads();                                       // As / Bs are rewritten by the next chunk
         }
-        __syncthreads();                                           // As is rewritten by the next offset
     }
     // epilogue: fragments -> shared (fp32) -> coalesced rows
     float *Cs = reinterpret_cast<float *>(smem_raw);               // [ROWS][16 * NT + 4]
@@ -133,27 +155,37 @@ conv_kernel(int n_out, int Cin, int Cout, int KV, const int *__restrict__ nbr, c
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
-// dW[o] (Cin x Cout) += sum_i in[nbr[o][i]]^T dout[i].  grid (voxel chunks, KV, (Cin/CTi) * (Cout/CTo)), CT = 64, 32 or 16
-// (the largest that divides the channel count); one CTA accumulates a CT x CT tile of dW[o] over its chunk of `rows_per_cta` output rows in
-// registers and adds it once with fp32 atomics.
-constexpr int WG_CT = 64;
-__host__ __device__ inline int wg_tile(int c) { return c % 64 == 0 ? 64 : c % 32 == 0 ? 32 : 16; }   // e.g. 96 = 3 x 32
-__global__ void __launch_bounds__(THREADS)
+// dW[o] (Cin x Cout) += sum_i in[nbr[o][i]]^T dout[i].  grid (voxel chunks, KV, (Cin/CTi) * (Cout/CTo)) with tiles of up to
+// 128 x 128 channels (one tile for the 32..128-channel layers: the gathered inputs and the output gradients are then read
+// once per (offset, row tile), not once per channel tile).  8 warps: warp w owns 16 input channels of the tile and all its
+// output columns; a CTA accumulates its tile over its chunk of `rows_per_cta` output rows in registers and adds it once
+// with fp32 atomics.
+constexpr int WG_MAX = 128;
+constexpr int WG_THREADS = 256;
+__host__ __device__ inline int wg_tile(int c) {             // largest multiple of 16 <= 128 that divides c
+    for (int t = WG_MAX; t >= 16; t -= 16)
+        if (c % t == 0) return t;
+    return 16;
+}
+
+__global__ void __launch_bounds__(WG_THREADS)
 wgrad_kernel(int n_out, int Cin, int Cout, int rows_per_cta, const int *__restrict__ nbr, const float *__restrict__ in,
              const float *__restrict__ dout, float *__restrict__ dw) {
-    __shared__ __align__(32) bf16 As[ROWS][WG_CT + PAD];           // gathered inputs  [voxel][cin tile]
-    __shared__ __align__(32) bf16 Ds[ROWS][WG_CT + PAD];           // output gradients [voxel][cout tile]
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int ci_t = wg_tile(Cin), co_t = wg_tile(Cout);
+    const int lda = ci_t + PAD, ldd = co_t + PAD;
+    bf16 *As = reinterpret_cast<bf16 *>(smem_raw);               // [ROWS][lda]  gathered inputs  (voxel, cin)
+    bf16 *Ds = As + ROWS * lda;                                  // [ROWS][ldd]  output gradients (voxel, cout)
     __shared__ int s_idx[ROWS];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int o = blockIdx.y;
-    const int ci_t = wg_tile(Cin), co_t = wg_tile(Cout);
     const int tiles_co = Cout / co_t;
     const int ci0 = (blockIdx.z / tiles_co) * ci_t, co0 = (blockIdx.z % tiles_co) * co_t;
-    const int nfr = co_t / 16;                                     // accumulator fragments per warp (<= 4)
-    const bool warp_on = warp * 16 < ci_t;                         // a 32-channel tile keeps two warps busy
-    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[4];
+    const int nfr = co_t / 16;                                   // accumulator fragments per warp (<= 8)
+    const bool warp_on = warp * 16 < ci_t;
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) wmma::fill_fragment(acc[j], 0.f);
+    for (int j = 0; j < 8; ++j) wmma::fill_fragment(acc[j], 0.f);
 
     const int r_begin = blockIdx.x * rows_per_cta, r_end = min(n_out, r_begin + rows_per_cta);
     for (int row0 = r_begin; row0 < r_end; row0 += ROWS) {
@@ -164,31 +196,37 @@ wgrad_kernel(int n_out, int Cin, int Cout, int rows_per_cta, const int *__restri
             s_idx[tid] = my;
         }
         if (!__syncthreads_or(my >= 0)) continue;
-        for (int e = tid; e < ROWS * (ci_t / 4); e += THREADS) {
+        for (int e = tid; e < ROWS * (ci_t / 4); e += WG_THREADS) {
             const int r = e / (ci_t / 4), c4 = e % (ci_t / 4);
             const int src = s_idx[r];
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (src >= 0) v = *reinterpret_cast<const float4 *>(in + (size_t)src * Cin + ci0 + 4 * c4);
-            As[r][4 * c4] = __float2bfloat16_rn(v.x); As[r][4 * c4 + 1] = __float2bfloat16_rn(v.y);
-            As[r][4 * c4 + 2] = __float2bfloat16_rn(v.z); As[r][4 * c4 + 3] = __float2bfloat16_rn(v.w);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const unsigned *>(&lo);
+            pk.y = *reinterpret_cast<const unsigned *>(&hi);
+            *reinterpret_cast<uint2 *>(As + r * lda + 4 * c4) = pk;
         }
-        for (int e = tid; e < ROWS * (co_t / 4); e += THREADS) {
+        for (int e = tid; e < ROWS * (co_t / 4); e += WG_THREADS) {
             const int r = e / (co_t / 4), c4 = e % (co_t / 4);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (s_idx[r] >= 0) v = *reinterpret_cast<const float4 *>(dout + (size_t)(row0 + r) * Cout + co0 + 4 * c4);
-            Ds[r][4 * c4] = __float2bfloat16_rn(v.x); Ds[r][4 * c4 + 1] = __float2bfloat16_rn(v.y);
-            Ds[r][4 * c4 + 2] = __float2bfloat16_rn(v.z); Ds[r][4 * c4 + 3] = __float2bfloat16_rn(v.w);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const unsigned *>(&lo);
+            pk.y = *reinterpret_cast<const unsigned *>(&hi);
+            *reinterpret_cast<uint2 *>(Ds + r * ldd + 4 * c4) = pk;
         }
         __syncthreads();
         if (warp_on) {
             for (int kv = 0; kv < ROWS; kv += 16) {                // the reduction dimension is the voxel axis
                 wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::col_major> af;      // (cin, voxel) = As^T
-                wmma::load_matrix_sync(af, &As[kv][warp * 16], WG_CT + PAD);
+                wmma::load_matrix_sync(af, As + kv * lda + warp * 16, lda);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     if (j < nfr) {
                         wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> bfr;
-                        wmma::load_matrix_sync(bfr, &Ds[kv][16 * j], WG_CT + PAD);
+                        wmma::load_matrix_sync(bfr, Ds + kv * ldd + 16 * j, ldd);
                         wmma::mma_sync(acc[j], af, bfr, acc[j]);
                     }
                 }
@@ -196,18 +234,20 @@ wgrad_kernel(int n_out, int Cin, int Cout, int rows_per_cta, const int *__restri
         }
         __syncthreads();
     }
-    // tile -> shared (reuse As/Ds storage as fp32 [64][64+4]) -> atomics
-    __shared__ float Ts[WG_CT][WG_CT + 4];
+    // tile -> shared fp32 (aliases the staging buffers) -> atomics
+    float *Ts = reinterpret_cast<float *>(smem_raw);               // [ci_t][co_t + 4]
+    const int ldt = co_t + 4;
+    __syncthreads();
     if (warp_on) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < nfr) wmma::store_matrix_sync(&Ts[warp * 16][16 * j], acc[j], WG_CT + 4, wmma::mem_row_major);
+        for (int j = 0; j < 8; ++j)
+            if (j < nfr) wmma::store_matrix_sync(Ts + (warp * 16) * ldt + 16 * j, acc[j], ldt, wmma::mem_row_major);
     }
     __syncthreads();
     float *dst = dw + (size_t)o * Cin * Cout;
-    for (int e = tid; e < ci_t * co_t; e += THREADS) {
+    for (int e = tid; e < ci_t * co_t; e += WG_THREADS) {
         const int r = e / co_t, c = e % co_t;
-        const float v = Ts[r][c];
+        const float v = Ts[r * ldt + c];
         if (v != 0.f) atomicAdd(dst + (size_t)(ci0 + r) * Cout + co0 + c, v);
     }
 }
@@ -215,7 +255,8 @@ wgrad_kernel(int n_out, int Cin, int Cout, int rows_per_cta, const int *__restri
 template <int NT>
 static int launch_conv(int n_out, int Cin, int Cout, int KV, const int *nbr, const float *in, const bf16 *w, float *out,
                        cudaStream_t st) {
-    const size_t smem = max((size_t)ROWS * (Cin + PAD) * sizeof(bf16), (size_t)ROWS * (16 * NT + 4) * sizeof(float));
+    const size_t smem = max((size_t)(ROWS * (KC + PAD) + KC * (16 * NT + PAD)) * sizeof(bf16),
+                            (size_t)ROWS * (16 * NT + 4) * sizeof(float));
     static size_t configured = 0;
     if (smem > configured) {
         UP3D_CUDA_OK(cudaFuncSetAttribute(conv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -271,13 +312,20 @@ extern "C" int up3d_sparse_conv_wgrad(int n_out, int c_in, int c_out, int kernel
     const int ci_t = sp::wg_tile(c_in), co_t = sp::wg_tile(c_out);
     if (n_out == 0) return 0;
     UP3D_CHECK_ARG(nbr && in && dout && dweight, "up3d_sparse_conv_wgrad: NULL pointer");
+    const size_t smem = max((size_t)sp::ROWS * (ci_t + sp::PAD + co_t + sp::PAD) * sizeof(sp::bf16),
+                            (size_t)ci_t * (co_t + 4) * sizeof(float));
+    static size_t configured = 0;
+    if (smem > configured) {
+        UP3D_CUDA_OK(cudaFuncSetAttribute(sp::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
     // enough voxel chunks to fill the machine, at least 4 sub-tiles each
     const int tiles = (c_in / ci_t) * (c_out / co_t);
-    int chunks = div_up(4 * UP3D_NUM_SMS, kernel_volume * tiles);
+    int chunks = div_up(3 * UP3D_NUM_SMS, kernel_volume * tiles);
     chunks = max(1, min(chunks, div_up(n_out, 4 * sp::ROWS)));
     const int rows_per_cta = div_up(div_up(n_out, chunks), sp::ROWS) * sp::ROWS;
     const dim3 grid(div_up(n_out, rows_per_cta), kernel_volume, tiles);
-    sp::wgrad_kernel<<<grid, sp::THREADS, 0, (cudaStream_t)stream>>>(n_out, c_in, c_out, rows_per_cta, nbr, in, dout, dweight);
+    sp::wgrad_kernel<<<grid, sp::WG_THREADS, smem, (cudaStream_t)stream>>>(n_out, c_in, c_out, rows_per_cta, nbr, in, dout, dweight);
     UP3D_LAUNCH_OK("sp::wgrad_kernel");
     return 0;
 }
