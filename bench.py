@@ -556,6 +556,30 @@ def ours(args):
                     "bf16-shadowed parameter; grad_sumsq_kernel (4 B/param) takes %.4f ms" % sq_ms}
     except Exception as e:
         extra["roofline_hbm_kernel_error"] = repr(e)
+    if rank == 0 and n_gpus == 1 and CFG_NAME.startswith("transformer"):
+        # two variants of the same step, each a fresh Trainer + CUDA graph, 10 resident-input replays (reported beside the
+        # headline, never instead of it): (i) backbone GEMMs in fp32 = the reference's precision (no AMP anywhere in its
+        # trainer); (ii) dense N(0,1) (B,128,R,R) image features in HBM instead of the analytic stem field
+        for key, kw, ov in (("variant_fp32_backbone", dict(autocast_dtype=None), []),
+                            ("variant_dense_randn_image_features", dict(autocast_dtype=autocast), ["model.image_branch=randn"])):
+            try:
+                from unipre3d_b200.config import compose as _compose
+                cfg_v = _compose(CFG_NAME, overrides=[f"data.training_resolution={RES}", f"opt.batch_size={OBJECTS_PER_GPU}"] + ov)
+                tv = Trainer(cfg_v, device=device, use_cuda_graph=True, **kw)
+                pb = tv.pack_batch(raw_batches[0])
+                for _ in range(3):
+                    tv.train_iteration(pb)
+                torch.cuda.synchronize()
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+                for a_, b_ in evs:
+                    flush.zero_()
+                    a_.record(); tv._graph.replay(); b_.record()
+                torch.cuda.synchronize()
+                msv = sum(a_.elapsed_time(b_) for a_, b_ in evs) / len(evs)
+                extra[key] = {"ms_per_step": msv, "views_per_s": views_per_step / (msv * 1e-3)}
+                del tv
+            except Exception as e:
+                extra[key + "_error"] = repr(e)
     if rank == 0:
         try:
             extra["raster_only"] = raster_only_headline(device, 5, peaks)
@@ -592,6 +616,7 @@ def ours(args):
                                        + ("configs[1])" if CFG_NAME.startswith("transformer") else "configs[2], per-GPU share)"),
                            "objects_per_gpu": OBJECTS_PER_GPU, "views_per_step": views_per_step, "parallelism": f"dp{n_gpus}",
                            "cuda_graph": bool(use_graph), "host_binding": binding,
+                           "value_excludes": "host-side StepLR bookkeeping and the EMA update (every 10th step); e2e includes them",
                            "host_images": ("float32 (divided by 255 on the host, as the reference loader)" if args.float_images
                                            else "uint8 as decoded from the dataset's PNGs; /255 on the device"),
                            "l2": "256 MiB buffer written between timed iterations (L2 flush), per-step CUDA-event pairs"},

@@ -102,6 +102,26 @@ class FrozenImageStem(nn.Module):
         return {"decoder_block_3": field if (lazy and x.is_cuda) else field.dense()}
 
 
+class RandnImageFeatures(nn.Module):
+    """`model.image_branch=randn`: the synthetic image features SURVEY.md §8d prescribes in place of the absent SD-VAE
+    weights -- a fixed N(0,1) (n,128,R,R) `decoder_block_3` tensor, materialised in HBM, which `image_conv` then reads
+    (GroupNorm statistics over the whole 268 MB tensor, 1x1 convolution at the sampled pixels)."""
+
+    def __init__(self, cfg, out_channels):
+        super().__init__()
+        self.cfg, self.out_channels = cfg, out_channels
+        self.encoder_config = {"block_out_channels": [128, 256, 512, 512]}
+        self._feat = None
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        n, _, H, W = x.shape
+        if self._feat is None or self._feat.shape != (n, 128, H, W) or self._feat.device != x.device:
+            g = torch.Generator(device=x.device).manual_seed(4321)
+            self._feat = torch.randn((n, 128, H, W), generator=g, device=x.device)
+        return {"decoder_block_3": self._feat}
+
+
 class SplatHeadFn(torch.autograd.Function):
     """`_process_network_output` (object level) + the SH concatenation of the renderer as one launch each way
     (csrc/head.cu).  raw (B,P,11+3M) fp32, center (B,P,3) -> xyz, opacity (B,P,1), scaling, rotation, shs (B,P,M,3)."""
@@ -239,8 +259,10 @@ class GaussianSplatPredictor(nn.Module):
                 self.image_network = ImageFeaturePredictor(cfg, [128], pretrained_path=getattr(cfg.model, "vae_weights", None))
             elif self.image_branch == "stem":
                 self.image_network = FrozenImageStem(cfg, [128])
+            elif self.image_branch == "randn":
+                self.image_network = RandnImageFeatures(cfg, [128])
             else:
-                raise ValueError(f"model.image_branch={self.image_branch!r} (expected 'stem' or 'sdvae')")
+                raise ValueError(f"model.image_branch={self.image_branch!r} (expected 'stem', 'randn' or 'sdvae')")
             self.point_network = PointFeaturePredictor(cfg, self.split_dimensions, pretrained_path=pretrained)
             mc = self.MODEL_CONFIGS[cfg.model.backbone_type]
             in_dim = self.image_network.encoder_config["block_out_channels"][0]
@@ -300,7 +322,7 @@ class GaussianSplatPredictor(nn.Module):
         if getattr(self.cfg.model, "dense_image_features", False):
             image_output = self.image_network.forward(image)
             image_features = self.image_conv.forward(image_output["decoder_block_3"])     # reference dataflow
-        elif self.image_branch == "sdvae":
+        elif self.image_branch in ("sdvae", "randn"):
             # dense (n,128,R,R) decoder features from the frozen VAE; image_conv is still evaluated only at the sampled pixels
             image_features = LazyImageFeatures(self.image_network.forward(image)["decoder_block_3"], self.image_conv)
         else:
