@@ -92,18 +92,27 @@ def _sync_worker(rank, world, port, out_dir, overlap):
         rest = [torch.nn.Parameter(torch.zeros(s)) for s in ((6,), (2, 9))]
         params = [rest[0]] + early + [rest[1]]                  # optimizer order differs from the flat-buffer order
         chunks = overlap == "chunks"
-        gs = GradSync(params, early, "cpu", overlap=bool(overlap))
+        direct = overlap == "direct"                            # the producer writes into the flat buffer (permuted layout)
+        gs = GradSync(params, early, "cpu", overlap=bool(overlap), early_order=[2, 0, 1] if direct else None)
+        if direct:
+            assert [s[0] for s in gs._early_slices] == [24, 24 + 35, 0]
         for step in range(2):                                   # two steps: buffers and handles are reused
             g = torch.Generator().manual_seed(100 * step + rank)
             eg = [torch.randn(p.shape, generator=g) for p in early]
             rg = [torch.randn(p.shape, generator=g) for p in rest]
-            if chunks:                                          # chunk-wise, last parameters first (backward order)
+            if direct:
+                views = gs._early_views()
+                for v, t in zip(views, eg):
+                    v.copy_(t)
+                got = gs.early_hook(views)                      # nothing to pack: same memory
+                assert all(a.data_ptr() == b.data_ptr() for a, b in zip(got, views))
+            elif chunks:                                        # chunk-wise, last parameters first (backward order)
                 gs.early_chunk_hook(2, eg[2:])
                 gs.early_chunk_hook(0, eg[:2])
                 got = eg
             else:
                 got = gs.early_hook(eg)                         # fires in the middle of the "backward"
-            assert all(a is b for a, b in zip(got, eg))
+            assert direct or all(a is b for a, b in zip(got, eg))
             for p, t in zip(early, got):
                 p.grad = t
             for p, t in zip(rest, rg):
@@ -120,7 +129,7 @@ def test_grad_sync_overlapped_all_reduce_sums_over_ranks():
     """grad_sync.GradSync (the N > 1 gradient exchange of the GPU trainer) over two gloo ranks: the early (in-backward)
     all-reduce on its own communicator + the tail all-reduce give the SUM over ranks, with and without the overlap."""
     world, shapes_e, shapes_r = 2, ((7, 5), (11,), (3, 4, 2)), ((6,), (2, 9))
-    for overlap in (True, False, "chunks"):
+    for overlap in (True, False, "chunks", "direct"):
         with tempfile.TemporaryDirectory() as td:
             mp.spawn(_sync_worker, args=(world, _free_port(), td, overlap), nprocs=world, join=True)
             got = torch.load(os.path.join(td, f"sync_{overlap}.pt"))

@@ -68,6 +68,20 @@ def _worker(rank, world, port, out_dir, use_graph):
             dist.destroy_process_group()
 
 
+def _spawn(fn, args, nprocs, deadline_s=420):
+    """mp.spawn with a deadline: a collective that never completes must fail this test, not hang the whole session."""
+    import time
+    import torch.multiprocessing as mp
+    ctx = mp.spawn(fn, args=args, nprocs=nprocs, join=False)
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > deadline_s:
+            for p in ctx.processes:
+                if p.is_alive():
+                    p.kill()
+            pytest.fail(f"data-parallel workers still running after {deadline_s} s")
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -77,11 +91,10 @@ def _free_port():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_two_gpu_sharded_step_equals_single_gpu_global_batch(use_graph):
-    import torch.multiprocessing as mp
     from unipre3d_b200 import synthetic
     from unipre3d_b200.trainer import Trainer
     with tempfile.TemporaryDirectory() as td:
-        mp.spawn(_worker, args=(2, _free_port(), td, use_graph), nprocs=2, join=True)
+        _spawn(_worker, (2, _free_port(), td, use_graph), 2)
         got = torch.load(os.path.join(td, "dp.pt"))
     cfg = _cfg(4)
     torch.manual_seed(0)

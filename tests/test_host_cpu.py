@@ -355,3 +355,14 @@ def test_scene_configs_compose_and_synthetic_scene_batch():
     assert key.unique().numel() == key.numel(), "one point per voxel"
     wv, vw = b["world_view_transforms"][1, 2], b["view_to_world_transforms"][1, 2]
     assert torch.allclose(wv @ vw, torch.eye(4), atol=1e-5)
+
+
+def test_stack_grad_order_is_the_backward_slab_layout():
+    """fused_encoder.stack_grad_order: the flat layout the data-parallel backward writes its gradients into -- four weight
+    slabs stacked over the blocks, then per block the column-sum gradients (n1w n1b bproj n2w n2b b2 | b1)."""
+    from unipre3d_b200 import fused_encoder as fe
+    depth, P = 3, fe.PARAMS_PER_BLOCK
+    order = fe.stack_grad_order(depth)
+    assert sorted(order) == list(range(depth * P))
+    assert order[:depth] == [2, 2 + P, 2 + 2 * P] and order[3 * depth:4 * depth] == [9, 9 + P, 9 + 2 * P]
+    assert order[4 * depth:4 * depth + 7] == [0, 1, 4, 5, 6, 10, 8]

@@ -116,12 +116,15 @@ def _wgrad(dy, x):
     return torch.mm(dy.t(), x, out_dtype=torch.float32)
 
 
-def _wgrad_batched(dy, x):
+def _wgrad_batched(dy, x, out=None):
     """(depth, T, out) x (depth, T, in) -> (depth, out, in) fp32: the weight gradients of one Linear of ALL blocks as a
-    single batched GEMM (16 launches of ~5 us become one)."""
+    single batched GEMM (16 launches of ~5 us become one).  `out`: where the GEMM writes (data parallel: the slab of the
+    gradient-exchange buffer, GRAD_BUFFERS)."""
     if dy.dtype == torch.float32:
-        return torch.bmm(dy.transpose(1, 2), x)
-    return torch.bmm(dy.transpose(1, 2), x, out_dtype=torch.float32)
+        return torch.bmm(dy.transpose(1, 2), x) if out is None else torch.bmm(dy.transpose(1, 2), x, out=out)
+    if out is None:
+        return torch.bmm(dy.transpose(1, 2), x, out_dtype=torch.float32)
+    return torch.bmm(dy.transpose(1, 2), x, out_dtype=torch.float32, out=out)
 
 
 def _linear_deep(x, w, b, tc):
@@ -155,6 +158,23 @@ GRAD_READY_HOOK = None
 # starting when the whole stack is done.
 GRAD_CHUNK_HOOK = None
 GRAD_CHUNK_BLOCKS = 4
+# Data parallel, zero-copy variant of GRAD_READY_HOOK: callable(depth, C, Hd) -> (gWqkv (depth,3C,C), gWproj (depth,C,C),
+# gW1 (depth,Hd,C), gW2 (depth,C,Hd), small (depth*(6C+Hd),)) fp32 slabs of the gradient-exchange buffer laid out as
+# stack_grad_order() says, or None.  The batched weight-gradient GEMMs and the column-sum kernels then write there
+# directly and the 113 MB pack in front of the all-reduce disappears.
+GRAD_BUFFERS = None
+
+
+def stack_grad_order(depth: int):
+    """Permutation of stack_parameters() that describes the flat layout GRAD_BUFFERS hands out: the four weight slabs
+    stacked over the blocks, then per block the column-sum gradients in the backward's `small` order."""
+    P = PARAMS_PER_BLOCK
+    order = []
+    for k in (2, 3, 7, 9):                           # qkv.weight, proj.weight, fc1.weight, fc2.weight
+        order += [i * P + k for i in range(depth)]
+    for i in range(depth):                           # n1w n1b bproj n2w n2b b2 | b1
+        order += [i * P + k for k in (0, 1, 4, 5, 6, 10, 8)]
+    return order
 
 
 class SideStream:
@@ -263,7 +283,11 @@ class EncoderStackFn(torch.autograd.Function):
             g = gout.reshape(T, C).contiguous().float()
             # all column-sum gradients of the stack in one zero-filled buffer (the kernels accumulate atomically)
             per = 6 * C + Hd      # n1w n1b bproj n2w n2b b2 (C each) + b1 (Hd)
-            small = torch.zeros(depth * per, dtype=torch.float32, device=dev)
+            bufs = GRAD_BUFFERS(depth, C, Hd) if (GRAD_BUFFERS is not None and GRAD_CHUNK_HOOK is None) else None
+            if bufs is not None:
+                small = bufs[4].zero_()
+            else:
+                small = torch.zeros(depth * per, dtype=torch.float32, device=dev)
             dpos = torch.zeros((T, C), dtype=torch.float32, device=dev)
             grads: List[Optional[torch.Tensor]] = [None] * (PARAMS_PER_BLOCK * depth)
 
@@ -323,8 +347,9 @@ class EncoderStackFn(torch.autograd.Function):
                     GRAD_CHUNK_HOOK(i, chunk)
             if not chunked:
                 # ---- weight gradients of all blocks: four batched GEMMs (fp32 written by the GEMM)
-                gW2, gW1 = _wgrad_batched(DD, HH), _wgrad_batched(DPRE, Y2)
-                gWproj, gWqkv = _wgrad_batched(DA, O), _wgrad_batched(DQKV, Y1)
+                oq, op, o1, o2 = bufs[:4] if bufs is not None else (None,) * 4
+                gW2, gW1 = _wgrad_batched(DD, HH, o2), _wgrad_batched(DPRE, Y2, o1)
+                gWproj, gWqkv = _wgrad_batched(DA, O, op), _wgrad_batched(DQKV, Y1, oq)
                 if tc:          # fc1 bias gradients of all blocks: one column-sum pass over the stacked dpre
                     small.view(depth, per)[:, 6 * C:].copy_(DPRE.sum(dim=1, dtype=torch.float32))
                 for i in range(depth):

@@ -23,7 +23,10 @@ import torch.distributed as dist
 
 class GradSync:
     def __init__(self, params: Sequence[torch.nn.Parameter], early_params: Sequence[torch.nn.Parameter], device,
-                 overlap: bool = True):
+                 overlap: bool = True, early_order: Sequence[int] = None):
+        """early_order: permutation of range(len(early_params)) = the order in which the early parameters lie in the
+        flat buffer (default: as given).  A producer that knows this layout can write its gradients straight into
+        `flat_early` (fused_encoder.GRAD_BUFFERS); early_hook then skips the pack for them."""
         self.world = dist.get_world_size()
         self.device = torch.device(device)
         early_ids = {id(p) for p in early_params}
@@ -33,8 +36,13 @@ class GradSync:
         self.flat = torch.zeros(n_early + n_rest, dtype=torch.float32, device=self.device)
         self.flat_early, self.flat_rest = self.flat[:n_early], self.flat[n_early:]
         self._early_slices, self._rest_views, off = [], [], 0
-        for p in self.early:
-            self._early_slices.append((off, off + p.numel(), tuple(p.shape)))
+        order = list(early_order) if early_order is not None else list(range(len(self.early)))
+        if sorted(order) != list(range(len(self.early))):
+            raise ValueError("early_order must be a permutation of the early parameters")
+        self._early_slices = [None] * len(self.early)
+        for k in order:
+            p = self.early[k]
+            self._early_slices[k] = (off, off + p.numel(), tuple(p.shape))
             off += p.numel()
         for p in self.rest:
             self._rest_views.append(self.flat[off: off + p.numel()].view_as(p))
@@ -65,12 +73,20 @@ class GradSync:
             self._pending.wait()
         self._pending = None
 
+    @staticmethod
+    def _pack(views, grads) -> None:
+        """Copy the gradients into their slices, except those the producer already wrote there."""
+        todo = [(v, g) for v, g in zip(views, grads)
+                if not (g.data_ptr() == v.data_ptr() and g.is_contiguous() and g.dtype == v.dtype)]
+        if todo:
+            torch._foreach_copy_([v for v, _ in todo], [g for _, g in todo])
+
     def early_hook(self, grads):
         """grads: the early parameters' gradients, in `early_params` order.  Returns what autograd should see."""
         if not self.overlap or len(grads) != len(self._early_slices):
             return grads
         self._join()                              # a previous backward that was never consumed (diagnostic passes)
-        torch._foreach_copy_(self._early_views(), list(grads))
+        self._pack(self._early_views(), grads)
         if self.is_cuda:
             self._comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._comm_stream):
@@ -107,7 +123,7 @@ class GradSync:
         if self._chunks_seen not in (0, len(self.early)):
             raise RuntimeError("chunked gradient exchange covered only part of the early parameters")
         if self._pending is None and self.early:  # the hook did not fire (module path / overlap off): reduce it now
-            torch._foreach_copy_(self._early_views(), [p.grad for p in self.early])
+            self._pack(self._early_views(), [p.grad for p in self.early])
             dist.all_reduce(self.flat_early, op=dist.ReduceOp.SUM)
         self._chunks_seen = 0
         if self.rest:

@@ -310,6 +310,7 @@ class Trainer:
             from . import fused_encoder
             fused_encoder.GRAD_READY_HOOK = None      # a hook left by an earlier data-parallel Trainer of this process
             fused_encoder.GRAD_CHUNK_HOOK = None
+            fused_encoder.GRAD_BUFFERS = None
         self.iteration = 0
         self._graph = None
         self._static: Optional[dict] = None
@@ -379,8 +380,22 @@ class Trainer:
         enc = getattr(getattr(self.model_manager.model, "point_network", None), "encoder", None)
         tb = getattr(getattr(enc, "blocks", None), "blocks", None)
         early = fused_encoder.stack_parameters(tb) if (tb is not None and fused_encoder.supports(tb)) else []
-        self._grad_sync = GradSync(self.params, early, self.device, overlap=not os.environ.get("UP3D_NO_EARLY_SYNC"))
+        direct = bool(early) and not os.environ.get("UP3D_NO_DIRECT_GRADS")
+        order = fused_encoder.stack_grad_order(len(tb)) if direct else None
+        self._grad_sync = GradSync(self.params, early, self.device, overlap=not os.environ.get("UP3D_NO_EARLY_SYNC"),
+                                   early_order=order)
         self.model_manager.optimizer.grad_scale = 1.0 / self.world
+        if direct:
+            # the stack's backward writes its gradients straight into the exchange buffer (no 113 MB pack)
+            flat = self._grad_sync.flat_early
+
+            def grad_buffers(depth, C, Hd):
+                sizes = [depth * 3 * C * C, depth * C * C, depth * Hd * C, depth * C * Hd, depth * (6 * C + Hd)]
+                if depth != len(tb) or sum(sizes) != flat.numel():
+                    return None
+                a, b, c, d, e = torch.split(flat, sizes)
+                return (a.view(depth, 3 * C, C), b.view(depth, C, C), c.view(depth, Hd, C), d.view(depth, C, Hd), e)
+            fused_encoder.GRAD_BUFFERS = grad_buffers
         if self._grad_sync.overlap:
             fused_encoder.GRAD_READY_HOOK = self._grad_sync.early_hook
             if os.environ.get("UP3D_CHUNKED_SYNC"):
