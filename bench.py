@@ -495,10 +495,15 @@ def ours(args):
         torch.cuda.synchronize()
 
         def step_resident(i):
-            trainer._graph.replay()
+            # one replay of the captured step: takes its FPS / ball-query grouping from the previous replay's tail
+            # branch and, beside its optimizer pass, groups the coordinates of the following step (the same work per
+            # step as train_iteration(..., prefetch=next))
+            trainer.replay_resident()
     else:
         def step_resident(i):
             trainer._step_body(resident)
+    for _ in range(2):
+        step_resident(0)                       # untimed: the first resident replay groups its batch in line
     with ClockSampler(local) as clk:
         ms_resident = timed(step_resident)
         # ---- end-to-end steps: pinned host batch -> H2D -> step -> D2H loss, through the public API
@@ -509,6 +514,19 @@ def ours(args):
         ms_e2e = timed(lambda i: losses.append(trainer.train_iteration(
             batches[i % n_batches], read_loss="lagged", prefetch=batches[(i + 1) % n_batches])))
         losses = [x for x in losses if x is not None] + [trainer.last_loss()]
+        # what this box's host->device path gives for one step's batch (median of 7 single copies from the pinned buffer):
+        # boxes of the pool differ from ~53 GB/s to ~2 GB/s here, which is what moves e2e relative to `value`
+        torch.cuda.synchronize()
+        probe_dst, probe_ms = torch.empty_like(resident_flat), []
+        for _ in range(7):
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            probe_dst.copy_(batches[0].flat, non_blocking=True)
+            p1.record()
+            torch.cuda.synchronize()
+            probe_ms.append(p0.elapsed_time(p1))
+        h2d_probe_gbs = h2d / (sorted(probe_ms)[3] * 1e-3) / 1e9
+        del probe_dst
         # steady state without the artificial L2 flush (the step's own working set -- parameters, moments, gradients,
         # shadows: ~520 MB -- already exceeds the 126 MB L2 several times over); reported next to the flushed headline
         barrier()
@@ -569,11 +587,12 @@ def ours(args):
                 pb = tv.pack_batch(raw_batches[0])
                 for _ in range(3):
                     tv.train_iteration(pb)
+                tv.replay_resident()
                 torch.cuda.synchronize()
                 evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
                 for a_, b_ in evs:
                     flush.zero_()
-                    a_.record(); tv._graph.replay(); b_.record()
+                    a_.record(); tv.replay_resident(); b_.record()
                 torch.cuda.synchronize()
                 msv = sum(a_.elapsed_time(b_) for a_, b_ in evs) / len(evs)
                 extra[key] = {"ms_per_step": msv, "views_per_s": views_per_step / (msv * 1e-3)}
@@ -616,6 +635,10 @@ def ours(args):
                                        + ("configs[1])" if CFG_NAME.startswith("transformer") else "configs[2], per-GPU share)"),
                            "objects_per_gpu": OBJECTS_PER_GPU, "views_per_step": views_per_step, "parallelism": f"dp{n_gpus}",
                            "cuda_graph": bool(use_graph), "host_binding": binding,
+                           "lookahead_grouping": ("every captured step groups (FPS + ball query) the following step's "
+                                                  "points in a branch beside its optimizer pass (steps served so far: %d)"
+                                                  % trainer.lookahead_hits
+                                                  if trainer._la is not None else "off"),
                            "value_excludes": "host-side StepLR bookkeeping and the EMA update (every 10th step); e2e includes them",
                            "host_images": ("float32 (divided by 255 on the host, as the reference loader)" if args.float_images
                                            else "uint8 as decoded from the dataset's PNGs; /255 on the device"),
@@ -623,7 +646,7 @@ def ours(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "views/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d * n_gpus, "d2h_bytes_per_step": 4 * n_gpus,
-                        "last_loss": losses[-1] if losses else None},
+                        "h2d_probe_GBs": h2d_probe_gbs, "last_loss": losses[-1] if losses else None},
                 "gpu_launches": gpu_launches, "cpu_baseline": cpu_baseline,
                 "steady_state_no_l2_flush": {"ms_per_step": ms_noflush, "views_per_s": views_per_step / (ms_noflush * 1e-3),
                                              "note": "same graph replays back to back, no flush between steps (not the "

@@ -140,3 +140,52 @@ def test_grad_sync_overlapped_all_reduce_sums_over_ranks():
             want = cur if want is None else [a + b for a, b in zip(want, cur)]
         for a, b in zip(got, want):
             assert torch.allclose(a, b, atol=1e-6)
+
+
+def _ready_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from unipre3d_b200.grad_sync import GradSync
+        early = [torch.nn.Parameter(torch.zeros(5, 3))]
+        # rest: r0 complete before the hook (ready); r1 gets a second contribution after it (late although it has a
+        # gradient at hook time); r2 only after the hook (late)
+        rest = [torch.nn.Parameter(torch.zeros(s)) for s in ((4,), (2, 3), (7,))]
+        gs = GradSync(rest[:1] + early + rest[1:], early, "cpu", overlap=True)
+        out = []
+        for step in range(3):
+            g = torch.Generator().manual_seed(10 * step + rank)
+            ge, g0, g1a, g1b, g2 = (torch.randn(s, generator=g) for s in ((5, 3), (4,), (2, 3), (2, 3), (7,)))
+            rest[0].grad, rest[1].grad = g0.clone(), g1a.clone()
+            gs.early_hook([ge])
+            rest[1].grad = rest[1].grad + g1b
+            rest[2].grad = g2.clone()
+            early[0].grad = ge
+            gs.finish()
+            assert gs.calibrated and gs._ready_idx == [0] and gs._late_idx == [1, 2]
+            out.append([p.grad.clone() for p in early + rest])
+            for p in early + rest:
+                p.grad = None
+        if rank == 0:
+            torch.save(out, os.path.join(out_dir, "ready.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_sync_ready_parameters_ride_with_the_early_all_reduce():
+    """Parameters whose gradients are final when the early hook fires are found by the calibration step and from then on
+    all-reduced together with the early ones; a parameter that still accumulates afterwards stays late.  Sums are right
+    on the calibration step and after it."""
+    world = 2
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_ready_worker, args=(world, _free_port(), td), nprocs=world, join=True)
+        got = torch.load(os.path.join(td, "ready.pt"))
+    for step in range(3):
+        want = None
+        for rank in range(world):
+            g = torch.Generator().manual_seed(10 * step + rank)
+            ge, g0, g1a, g1b, g2 = (torch.randn(s, generator=g) for s in ((5, 3), (4,), (2, 3), (2, 3), (7,)))
+            cur = [ge, g0, g1a + g1b, g2]
+            want = cur if want is None else [a + b for a, b in zip(want, cur)]
+        for a, b in zip(got[step], want):
+            assert torch.allclose(a, b, atol=1e-6), step

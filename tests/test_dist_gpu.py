@@ -51,6 +51,10 @@ def _worker(rank, world, port, out_dir, use_graph):
         assert tr.world == 2 and tr.bs_per_gpu == 2
         batches = [shard_batch(synthetic.make_batch(cfg, 4, 1024, seed=10 + s), rank, world) for s in range(STEPS)]
         losses, m1, bn = _run_steps(tr, batches)
+        gs = tr._grad_sync
+        # the calibration step found the parameters downstream of the stack (their gradients leave with the early
+        # all-reduce) and left the tokenizer in front of it for the tail
+        assert gs.calibrated and len(gs._ready_idx) > 0 and len(gs._late_idx) > 0, (len(gs._ready_idx), len(gs._late_idx))
         t = torch.tensor(losses, device="cuda")
         dist.all_reduce(t)
         if rank == 0:

@@ -95,6 +95,41 @@ def test_cuda_graph_step_matches_eager_and_learns():
     assert abs(losses[True][0] - losses[False][0]) <= 1e-5 * abs(losses[False][0]) + 1e-7
 
 
+@pytest.mark.parametrize("packed", [True, False])
+def test_lookahead_grouping_equals_inline_grouping(packed):
+    """Graph mode with `prefetch`: the FPS / ball-query grouping of batch i+1 is computed on a side stream next to step i
+    and consumed by step i+1.  Same losses as eager steps that group in line, on a DIFFERENT batch every step (a stale or
+    mismatched grouping would change the loss at once); then `replay_resident` (bench.py's `value` loop) on the last batch."""
+    from unipre3d_b200 import synthetic
+    from unipre3d_b200.trainer import Trainer
+    cfg = _cfg(res=64, bs=2)
+    batches = [synthetic.make_batch(cfg, 2, 1024, seed=20 + i, pin=True) for i in range(5)]
+    losses = {}
+    for mode in (False, True):
+        torch.manual_seed(0)
+        tr = Trainer(cfg, use_cuda_graph=mode)
+        for blk in tr.model_manager.model.modules():
+            if blk.__class__.__name__ == "DropPath":
+                blk.drop_prob = 0.0
+        if mode:
+            bs = [tr.pack_batch(b) for b in batches] if packed else batches
+            losses[mode] = [tr.train_iteration(bs[i], prefetch=bs[i + 1] if i + 1 < len(bs) else None)
+                            for i in range(len(bs))]
+            assert tr._la is not None and tr.lookahead_hits == len(bs) - 1
+            assert tr.model_manager.model.point_network.encoder.group_divider.lookahead is None   # capture-only hook
+            # resident replays: same batch again and again -> the loss keeps falling, grouping comes from the side stream
+            hits = tr.lookahead_hits
+            for _ in range(3):
+                tr.replay_resident()
+            torch.cuda.synchronize()
+            assert tr.lookahead_hits == hits + 2 and float(tr._loss_buf) < losses[mode][-1]
+        else:
+            losses[mode] = [tr.train_iteration(b) for b in batches]
+    assert abs(losses[True][0] - losses[False][0]) <= 1e-5 * abs(losses[False][0]) + 1e-7
+    for a, b in zip(losses[True], losses[False]):
+        assert abs(a - b) <= 2e-3 * abs(b) + 1e-5, (losses[True], losses[False])
+
+
 def test_lazy_image_features_equal_dense_dataflow():
     """Sampling Conv1x1(GroupNorm(features)) at the projected pixels == indexing the dense tensor
     (the reference's dataflow, gaussian_predictor.py:139 + feat_fusion.py:121-131): values and parameter gradients."""

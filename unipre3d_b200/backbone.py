@@ -182,10 +182,24 @@ class SubsampleGroup(nn.Module):
         if not ("ball" in group.lower() or "query" in group.lower()):
             raise NotImplementedError(f"{group.lower()} is not implemented. Only support ballquery")
 
+        # Set by trainer.Trainer ONLY while it captures its step graph: (neighborhood, center) static tensors that hold
+        # the grouping of the step's batch, computed ahead of the step (FPS + ball query depend on the input coordinates
+        # alone, so the trainer runs them for batch i+1 next to step i).  None everywhere else: forward() then groups inline.
+        self.lookahead = None
+
+    def group(self, p, out=None):
+        """FPS + ball-query grouping of p (B,N,3) -> (neighborhood (B,3,G,K), center (B,G,3))."""
+        return pointops.subsample_group(p, self.num_groups, self.group_size, self.radius, out=out)
+
     def forward(self, p, x=None):
         if x is not None:
             raise NotImplementedError("feature grouping is not on the render-loss path (transformer.py:305)")
-        return pointops.subsample_group(p, self.num_groups, self.group_size, self.radius)
+        if self.lookahead is not None:
+            neigh, center = self.lookahead
+            if neigh.shape[0] != p.shape[0] or neigh.device != p.device:
+                raise RuntimeError("SubsampleGroup.lookahead does not belong to this batch")
+            return neigh, center
+        return self.group(p)
 
 
 class PointTransformerEncoder(nn.Module):

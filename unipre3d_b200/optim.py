@@ -104,12 +104,22 @@ class FusedClipAdamW(torch.optim.AdamW):
         # (data-parallel mode: every p.grad is a fixed view of GradSync's flat buffer)
         self._last_ptrs = None
         self._ring, self._ring_ev, self._ring_i = [], [], 0
+        self._side = torch.cuda.Stream(device=dev)      # carries the captured pointer-table upload (mark_step_start)
         self._built = True
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._built = False                    # moments were replaced: rebuild the pointer tables at the next step
         self._last_ptrs = None                 # ... and re-upload the gradient pointers into the new table
+
+    def mark_step_start(self) -> None:
+        """Called by the trainer at the top of a step that is being captured: the pointer-table upload of this step (a
+        memcpy node whose content does not depend on anything the step computes) is then attached to this point of the
+        graph instead of the end of the backward, which takes its ~10 us launch latency off the critical path."""
+        self._start_ev = None
+        if getattr(self, "_built", False) and torch.cuda.is_current_stream_capturing():
+            self._start_ev = torch.cuda.Event()
+            self._start_ev.record()
 
     def _upload_grad_ptrs(self) -> None:
         """The gradient tensors are re-allocated by autograd every step (at fixed graph-pool addresses under CUDA-graph
@@ -126,7 +136,16 @@ class FusedClipAdamW(torch.optim.AdamW):
             buf = self._capture_bufs.pop()
             buf.copy_(torch.tensor(ptrs, dtype=torch.int64))
             self._frozen.append(buf)
-            self._g_ptrs.copy_(buf, non_blocking=True)
+            ev = getattr(self, "_start_ev", None)
+            if ev is not None:
+                cur = torch.cuda.current_stream()
+                self._side.wait_event(ev)
+                with torch.cuda.stream(self._side):
+                    self._g_ptrs.copy_(buf, non_blocking=True)
+                cur.wait_stream(self._side)
+                self._start_ev = None
+            else:
+                self._g_ptrs.copy_(buf, non_blocking=True)
             self._last_ptrs = None
             return
         if len(self._ring) < 4:

@@ -123,17 +123,25 @@ class GroupingOperation(Function):
 grouping_operation = GroupingOperation.apply
 
 
-def subsample_group(xyz: torch.Tensor, num_groups: int, group_size: int, radius: float, return_idx: bool = False):
+def subsample_group(xyz: torch.Tensor, num_groups: int, group_size: int, radius: float, return_idx: bool = False,
+                    out=None):
     """Fused SubsampleGroup.forward (group_embed.py:39-57 with the ball-query grouper): FPS -> centres ->
     ball query -> grouped, centred coordinates.  xyz (B,N,3) -> neighborhood (B,3,G,K), center (B,G,3).
-    xyz carries no gradient on the reference's path (raw input coordinates), so neither do the outputs."""
+    xyz carries no gradient on the reference's path (raw input coordinates), so neither do the outputs.
+    `out` = (neighborhood, center): contiguous fp32 tensors to write into."""
     require_cuda(xyz)
     xyz = xyz.contiguous().float()
     B, N, _ = xyz.shape
     with torch.no_grad():
         fidx = furthest_point_sample(xyz, num_groups)
-        center = torch.empty((B, num_groups, 3), dtype=torch.float32, device=xyz.device)
-        neigh = torch.empty((B, 3, num_groups, group_size), dtype=torch.float32, device=xyz.device)
+        if out is not None:
+            neigh, center = out
+            if not (tuple(neigh.shape) == (B, 3, num_groups, group_size) and tuple(center.shape) == (B, num_groups, 3)
+                    and neigh.dtype == center.dtype == torch.float32 and neigh.is_contiguous() and center.is_contiguous()):
+                raise ValueError("subsample_group: `out` must be contiguous fp32 (B,3,G,K) and (B,G,3) tensors")
+        else:
+            center = torch.empty((B, num_groups, 3), dtype=torch.float32, device=xyz.device)
+            neigh = torch.empty((B, 3, num_groups, group_size), dtype=torch.float32, device=xyz.device)
         idx = torch.empty((B, num_groups, group_size), dtype=torch.int32, device=xyz.device) if return_idx else None
         with torch.cuda.device(xyz.device):
             check(_lib.lib.up3d_subsample_group(B, N, num_groups, group_size, float(radius), ptr(xyz), ptr(fidx),

@@ -328,6 +328,11 @@ class Trainer:
         self._staged = None          # (key, device dict | flat device buffer, ready event)
         self._stage_flat = None      # device image of the PackedBatch being prefetched
         self._static_flat = None     # flat device buffer behind the captured graph's static inputs
+        # lookahead grouping (graph mode, object-level transformer): the step graph groups (FPS + ball query) the NEXT
+        # batch's points in a branch beside its optimizer pass and reads its own grouping from static tensors
+        # (see _lookahead_setup)
+        self._la = None
+        self.lookahead_hits = 0      # steps whose grouping had been computed ahead (diagnostics / tests)
 
     def _lpips_due(self, iteration: int) -> bool:
         """train_network.py:229-231, 288-296: the LPIPS term joins the loss after opt.start_lpips_after."""
@@ -338,7 +343,7 @@ class Trainer:
         captured graph (parameter / moment / pointer tables) is dropped and re-captured at the next iteration."""
         info = self.model_manager.load_checkpoint(path, load_optimizer=load_optimizer)
         self.iteration = info["iteration"]
-        self._graph, self._static, self._staged, self._static_flat = None, None, None, None
+        self._graph, self._static, self._staged, self._static_flat, self._la = None, None, None, None, None
         return info
 
     # ---------------------------------------------------------------------------------------------
@@ -355,7 +360,8 @@ class Trainer:
             gt = gt.float().div(255.0) if gt.dtype == torch.uint8 else gt
         return rendered.reshape(-1, *rendered.shape[2:]), gt
 
-    def _forward_backward(self, data) -> torch.Tensor:
+    def _forward_backward(self, data, after_forward=None) -> torch.Tensor:
+        """`after_forward`: called once the backbone's forward has been enqueued (lookahead grouping forks there)."""
         mm = self.model_manager
         model_inputs = prepare_model_inputs(data, self.cfg, self.bs_per_gpu, self.device)
         mm.forward_model.train()
@@ -365,6 +371,8 @@ class Trainer:
             splats = {k: ([t.float() for t in v] if isinstance(v, (list, tuple)) else v.float()) for k, v in splats.items()}
         else:
             splats = mm.forward_model(**model_inputs)
+        if after_forward is not None:
+            after_forward()
         rendered, gt = self.render_validation_views(splats, data)
         loss = self.validation_manager.calculate_losses(rendered, gt, self.iteration)["total_loss"]
         loss.backward()
@@ -387,9 +395,10 @@ class Trainer:
         self.model_manager.optimizer.grad_scale = 1.0 / self.world
         if direct:
             # the stack's backward writes its gradients straight into the exchange buffer (no 113 MB pack)
-            flat = self._grad_sync.flat_early
+            gs_ = self._grad_sync
 
             def grad_buffers(depth, C, Hd):
+                flat = gs_.flat_early
                 sizes = [depth * 3 * C * C, depth * C * C, depth * Hd * C, depth * C * Hd, depth * (6 * C + Hd)]
                 if depth != len(tb) or sum(sizes) != flat.numel():
                     return None
@@ -424,9 +433,25 @@ class Trainer:
         mm.optimizer.zero_grad(set_to_none=True)   # grads are re-materialised at the same graph-pool addresses on replay
 
     def _step_body(self, data) -> torch.Tensor:
-        loss = self._forward_backward(data)
+        mark = getattr(self.model_manager.optimizer, "mark_step_start", None)
+        if mark is not None:
+            mark()
+        la = self._lookahead_graph_head()
+        fork = None
+        if la is not None:
+            def fork():
+                # grouping of the next batch as a branch that starts when the backbone's forward is done and runs beside
+                # the rasterizer / loss / backward (measured placements: beside the tokenizer at the head of the step it
+                # slowed those latency-bound kernels by as much as it saved; beside the optimizer pass it took 230 us
+                # against the optimizer's 170 us)
+                la["branch"].wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(la["branch"]):
+                    la["module"].group(la["next_points"], out=la["next"])
+        loss = self._forward_backward(data, after_forward=fork)
         self._allreduce_grads()
         self._clip_and_step()
+        if la is not None:
+            torch.cuda.current_stream().wait_stream(la["branch"])
         return loss
 
     @torch.no_grad()
@@ -465,6 +490,8 @@ class Trainer:
 
     # ---------------------------------------------------------------------------------------------
     def _copy_into_static(self, data) -> None:
+        if self._la is not None and self._la["for"] is Trainer._RESIDENT:
+            self._la["for"] = None                                      # the resident batch is being replaced
         if torch.is_tensor(data):                                       # flat device image of a PackedBatch
             if self._static_flat is None:
                 raise RuntimeError("the step graph was captured from an unpacked batch; pass the same kind every step")
@@ -478,6 +505,112 @@ class Trainer:
             else:
                 dst.copy_(src, non_blocking=True)
         cp(self._static, data)
+
+    # ------------------------------------------------------------------------------------------ lookahead grouping
+    # FPS + ball-query grouping depends on the input coordinates alone and is a 140 us chain of latency-bound kernels on
+    # 16 SMs at the head of every step.  In graph mode the captured step therefore (1) starts by taking its grouping from
+    # the static tensors `next` (one small D2D copy into `cur`), and (2) carries a branch, forked after the backbone's
+    # forward, that groups the points in the static buffer `next_points` into `next` for the step after it.
+    # train_iteration(data, prefetch=nxt) feeds `next_points` with nxt's coordinates; when a step's grouping was not
+    # prepared that way (first step, no prefetch) it is computed in line before the replay, as without the lookahead.
+    _RESIDENT = object()
+
+    @staticmethod
+    def _points_of(batch):
+        pc = batch["point_cloud"]
+        pts = pc["pos"] if isinstance(pc, dict) else pc
+        return pts[:, :, :3]
+
+    def _lookahead_setup(self) -> None:
+        """Off (None) for backbones without a SubsampleGroup tokenizer or with UP3D_NO_LOOKAHEAD=1."""
+        from .backbone import SubsampleGroup
+        enc = getattr(getattr(self.model_manager.model, "point_network", None), "encoder", None)
+        gd = getattr(enc, "group_divider", None)
+        if not isinstance(gd, SubsampleGroup) or os.environ.get("UP3D_NO_LOOKAHEAD"):
+            self._la = None
+            return
+        pts = self._points_of(self._static)
+        B, N = pts.shape[0], pts.shape[1]
+        n_neigh, n_center = B * 3 * gd.num_groups * gd.group_size, B * gd.num_groups * 3
+
+        def pair():
+            flat = torch.empty(n_neigh + n_center, dtype=torch.float32, device=self.device)
+            return flat, (flat[:n_neigh].view(B, 3, gd.num_groups, gd.group_size), flat[n_neigh:].view(B, gd.num_groups, 3))
+        cur_flat, cur = pair()
+        nxt_flat, nxt = pair()
+        self._la = {"module": gd, "cur_flat": cur_flat, "cur": cur, "next_flat": nxt_flat, "next": nxt,
+                    "next_points": pts.float().contiguous().clone(),          # (B,N,3) fp32, read by the graph's tail
+                    "pts_stage": None, "pts_ready": None, "pts_free": None,  # host->device staging of the next points
+                    "branch": torch.cuda.Stream(device=self.device), "h2d": torch.cuda.Stream(device=self.device),
+                    "for": None}
+        gd.group(self._la["next_points"], out=nxt)                            # the first replay takes it from `next`
+
+    def _lookahead_feed(self, prefetch) -> None:
+        """Host side, top of a step: start the H2D copy of the NEXT batch's coordinates into the staging buffer (its own
+        stream; it waits only for the previous consumer of the staging buffer, so it runs while the previous step does)."""
+        la = self._la
+        host = self._points_of(prefetch.data if isinstance(prefetch, PackedBatch) else prefetch)
+        if host.is_cuda:
+            la["pts_stage"], la["pts_ready"] = host, None
+            return
+        if not host.is_contiguous():
+            host = host.contiguous()
+        if la["pts_stage"] is None or la["pts_stage"].shape != host.shape or la["pts_stage"].dtype != host.dtype or \
+                not la["pts_stage"].is_contiguous():
+            la["pts_stage"] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+            la["pts_free"] = None
+        st = la["h2d"]
+        if la["pts_free"] is not None:
+            st.wait_event(la["pts_free"])
+        with torch.cuda.stream(st):
+            la["pts_stage"].copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        la["pts_ready"] = ev
+
+    def _lookahead_before_replay(self, key, prefetch) -> None:
+        """Current stream, after the step's inputs are in the static buffers: make `next` hold THIS batch's grouping (it
+        does when the previous replay's tail was fed with it; else group in line) and `next_points` the next batch's
+        coordinates for this replay's tail."""
+        la = self._la
+        cur = torch.cuda.current_stream()
+        if la["for"] is not None and la["for"] is key:
+            self.lookahead_hits += 1
+        else:
+            la["module"].group(self._points_of(self._static), out=la["next"])
+        if prefetch is not None:
+            if la["pts_ready"] is not None:
+                cur.wait_event(la["pts_ready"])
+            la["next_points"].copy_(la["pts_stage"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            la["pts_free"] = ev
+        # without a prefetch the tail regroups whatever `next_points` holds; the result is not used (for = None)
+        la["for"] = prefetch
+
+    def _lookahead_graph_head(self):
+        """Inside the captured step: cur <- next.  Returns the lookahead state when it is active for this capture."""
+        la = self._la
+        if la is None or la["module"].lookahead is None:
+            return None
+        la["cur_flat"].copy_(la["next_flat"], non_blocking=True)
+        return la
+
+    def replay_resident(self) -> None:
+        """One step on the batch already resident in the graph's static inputs (bench.py's `value`): the replay takes its
+        grouping from the previous replay's tail branch and regroups the same coordinates for the next one."""
+        if self._graph is None:
+            raise RuntimeError("replay_resident needs a captured step (run train_iteration once in graph mode)")
+        la = self._la
+        if la is not None:
+            if la["for"] is Trainer._RESIDENT:
+                self.lookahead_hits += 1
+            else:
+                pts = self._points_of(self._static)
+                la["next_points"].copy_(pts, non_blocking=True)
+                la["module"].group(pts, out=la["next"])
+                la["for"] = Trainer._RESIDENT
+        self._graph.replay()
 
     def pack_batch(self, data) -> PackedBatch:
         """Host batch dict -> PackedBatch (one flat pinned buffer): the form `train_iteration` moves with ONE H2D copy."""
@@ -547,21 +680,33 @@ class Trainer:
                 # warm-up steps are real optimizer steps on the first batch: model, BatchNorm buffers, optimizer
                 # moments and the step counter are snapshotted and put back, so iteration 1 starts from the same state
                 # as in eager mode (only the RNG stream has advanced).
-                snap = self._snapshot_state()
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    for _ in range(3):
-                        self._step_body(self._static)
-                torch.cuda.current_stream().wait_stream(s)
-                torch.cuda.synchronize()
-                self._restore_state(snap)
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
-                    self._loss_buf.copy_(self._step_body(self._static))
+                self._lookahead_setup()
+                gd = self._la["module"] if self._la is not None else None
+                try:
+                    if gd is not None:
+                        gd.lookahead = self._la["cur"]      # only while warming up / capturing (see SubsampleGroup)
+                    snap = self._snapshot_state()
+                    s = torch.cuda.Stream()
+                    s.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(s):
+                        for _ in range(3):
+                            self._step_body(self._static)
+                    torch.cuda.current_stream().wait_stream(s)
+                    torch.cuda.synchronize()
+                    self._restore_state(snap)
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+                        self._loss_buf.copy_(self._step_body(self._static))
+                finally:
+                    if gd is not None:
+                        gd.lookahead = None
             if isinstance(data, PackedBatch) and getattr(self, "_static_sig", None) != data.signature():
                 raise RuntimeError("PackedBatch layout differs from the one the step graph was captured with")
+            if self._la is not None and prefetch is not None:
+                self._lookahead_feed(prefetch)                  # the next batch's coordinates start moving first
             self._copy_into_static(self._take_staged(data))     # D2D when prefetched, H2D otherwise
+            if self._la is not None:
+                self._lookahead_before_replay(data, prefetch)
             if prefetch is not None:
                 self._stage(prefetch)
             self._graph.replay()
