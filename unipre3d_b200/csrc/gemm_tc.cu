@@ -40,8 +40,16 @@ namespace tc {
 constexpr int BM = 128;      // rows per CTA tile = TMEM lanes
 constexpr int BK = 64;       // K elements per ring stage = one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;   // K per tcgen05.mma (32 bytes / sizeof(bf16))
-constexpr int THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
-constexpr int EPI_THREADS = 256;
+// warp 0 TMA, warp 1 MMA, then EPI_WPQ epilogue warps per TMEM lane quarter.  The epilogue (TMEM -> bias / GELU -> bf16 ->
+// staging -> TMA store) is the longest serial piece of a one-tile-per-SM launch: with two warps per quarter a thread
+// walked 64 columns of GELU (3.7 us of an isolated 10.7 us fc1 + GELU launch, tools/bench_tc_instep.py); four per quarter
+// give every 32-column chunk of a 96/128-wide tile its own warp.
+#ifndef UP3D_TC_EPI_WPQ
+#define UP3D_TC_EPI_WPQ 4
+#endif
+constexpr int EPI_WPQ = UP3D_TC_EPI_WPQ;
+constexpr int EPI_THREADS = 128 * EPI_WPQ;
+constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 enum { B_KMAJOR = 0, B_NMAJOR = 1 };
@@ -340,7 +348,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else {
         // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31; thread = one output row
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;            // the two warps of a lane quarter alternate over the 32-column chunks
+        const int half = (warp - 2) >> 2;            // the EPI_WPQ warps of a lane quarter take the 32-column chunks in turn
         const int r = 32 * q + lane;
         if (EPI == EPI_GELU_BWD) mbar_wait(aux_bar, 0);
         mbar_wait(accum_bar, 0);
@@ -348,7 +356,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (KS > 1) {
             // park this CTA's partial tile (fp32, swizzled 32-column chunks) in the now idle ring
 #pragma unroll 1
-            for (int c = half; c < BN / 32; c += 2) {
+            for (int c = half; c < BN / 32; c += EPI_WPQ) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
 #pragma unroll
@@ -357,7 +365,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         } else
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += EPI_WPQ) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
             float f[32];
