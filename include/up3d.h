@@ -318,6 +318,11 @@ UP3D_API int up3d_bn_reduce_finalize(int n_partials, int C, const float *partial
                                      const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
                                      float *running_var, int64_t *num_batches_tracked, float *triple_out, float *stats,
                                      up3d_stream_t stream);
+/* The group-tile passes below stream whole group tiles through a shared-memory ring (cp.async.bulk + mbarrier) when the
+ * tile layout allows it; up3d_set_group_tile_staging(0) selects the direct-load variant instead (same arithmetic, bit-identical
+ * results; UP3D_GT_STAGED=0 in the environment does the same).  Returns the previous setting.  No reference counterpart. */
+UP3D_API int up3d_set_group_tile_staging(int on);
+
 /* BatchNorm over z = zl + gpart[g] + bias (zl (R,C): the local half of Conv1d(512,512) on [global || local]
  * (transformer.py:236-238); gpart (Gt,C) fp32: the global half, one row per group; both optional):
  *   stats      : partials (ceil(Gt/gpc), 3, C) = [shift, sum (z-shift), sum (z-shift)^2], gpc*K rows per partial

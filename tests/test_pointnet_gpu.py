@@ -122,3 +122,31 @@ def test_group_combine_matches_torch():
         ref = dl.view(Gt, K, C) + torch.zeros(Gt, K, C, device=DEV).scatter_(1, arg.long().unsqueeze(1), dp.unsqueeze(1))
         assert torch.allclose(dx.view(Gt, K, C), ref, atol=1e-6)
         assert torch.allclose(cs, ref.sum((0, 1)), atol=1e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,G", [(8, 128), (5, 100)])
+def test_staged_group_tile_passes_are_bit_identical_to_direct_loads(B, G):
+    """bf16 mini-PointNet, forward + backward: the shared-memory-ring variant of the group-tile kernels (cp.async.bulk,
+    several groups per CTA, ragged last CTA) == the direct-load variant bit for bit -- outputs, every parameter gradient
+    and the BatchNorm running statistics."""
+    from unipre3d_b200 import _lib
+    torch.manual_seed(5)
+    nb = torch.randn(B, 3, G, 32, device=DEV) * 0.05
+    w = torch.randn(B, G, 384, device=DEV)
+    res = {}
+    prev = _lib.lib.up3d_set_group_tile_staging(1)
+    try:
+        for staged in (1, 0):
+            _lib.lib.up3d_set_group_tile_staging(staged)
+            enc = _encoder(seed=7)
+            enc.train()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = enc.forward_grouped(nb)
+            (out.float() * w).sum().backward()
+            res[staged] = ([out.detach().clone()] + [p.grad.clone() for p in enc.parameters()] +
+                           [b.clone() for b in enc.buffers()])
+    finally:
+        _lib.lib.up3d_set_group_tile_staging(prev)
+    assert len(res[0]) == len(res[1]) > 10
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)

@@ -85,6 +85,7 @@ def _load() -> C.CDLL:
         "up3d_adamw_apply": (i32, [i32, i32] + [vp] * 10 + [f32] * 6 + [vp, vp]),
         "up3d_grad_sumsq": (i32, [i32, i32] + [vp] * 4 + [f32, vp, vp]),
         "up3d_set_pdl": (i32, [i32]),
+        "up3d_set_group_tile_staging": (i32, [i32]),
         "up3d_sparse_subm_rulebook": (i32, [i32, i32, vp, vp, vp, vp]),
         "up3d_sparse_conv": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp]),
         "up3d_sparse_conv_wgrad": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp]),
@@ -110,7 +111,7 @@ EXPORTED = ["up3d_last_error", "up3d_version", "up3d_fps", "up3d_fps_max_residen
             "up3d_bn_reduce_finalize", "up3d_gbn_stats", "up3d_gbn_apply_relu", "up3d_gbn_bwd_reduce", "up3d_gbn_bwd_apply",
             "up3d_group_max", "up3d_group_max_scatter", "up3d_group_combine", "up3d_attn_max_len", "up3d_attn_fwd",
             "up3d_attn_bwd", "up3d_splat_head_fwd", "up3d_splat_head_bwd", "up3d_fusion_project",
-            "up3d_zorder_keys", "up3d_hilbert_keys", "up3d_tc_linear", "up3d_set_pdl", "up3d_sparse_subm_rulebook",
+            "up3d_zorder_keys", "up3d_hilbert_keys", "up3d_tc_linear", "up3d_set_pdl", "up3d_set_group_tile_staging", "up3d_sparse_subm_rulebook",
             "up3d_sparse_conv", "up3d_sparse_conv_wgrad"]
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)

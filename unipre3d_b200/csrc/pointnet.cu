@@ -14,22 +14,30 @@
 // Rows are (group, k): r = g*K + k, g < Gt = B*G.  Activations between GEMMs are AT = float or __nv_bfloat16.
 #include <cuda_bf16.h>
 
+#include <atomic>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace up3d {
 
 template <typename AT> struct PVec4;
 template <> struct PVec4<float> {
+    using Raw = float4;               // what a load leaves in registers until the value is used
+    static __device__ __forceinline__ Raw load_raw(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+    static __device__ __forceinline__ float4 cvt(Raw r) { return r; }
     static __device__ __forceinline__ float4 load(const float *p) { return *reinterpret_cast<const float4 *>(p); }
     static __device__ __forceinline__ void store(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 };
 template <> struct PVec4<__nv_bfloat16> {
-    static __device__ __forceinline__ float4 load(const __nv_bfloat16 *p) {
-        const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    using Raw = uint2;                // 4 packed bf16: batches of in-flight loads cost half the registers of float4
+    static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint2 *>(p); }
+    static __device__ __forceinline__ float4 cvt(Raw r) {
         const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
         const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
         return make_float4(fa.x, fa.y, fb.x, fb.y);
     }
+    static __device__ __forceinline__ float4 load(const __nv_bfloat16 *p) { return cvt(load_raw(p)); }
     static __device__ __forceinline__ void store(__nv_bfloat16 *p, float4 v) {
         const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
         uint2 r;
@@ -263,7 +271,15 @@ bn_reduce_finalize_kernel(int nPart, int C, const float *__restrict__ partials, 
 // CTA = `gpc` consecutive groups x one column tile; blockDim = (CT column threads, RL row lanes); a column thread owns
 // 4 consecutive columns; row lane l handles rows k = l, l+RL, ... of each group.
 constexpr int GT_RL = 4;
-constexpr int GT_MAXK = 64;       // rows of a group handled per lane are unrolled in batches of 8
+constexpr int GT_MAXK = 64;
+#ifndef UP3D_GT_BATCH
+#define UP3D_GT_BATCH 8
+#endif
+#ifndef UP3D_GT_MIN_CTAS
+#define UP3D_GT_MIN_CTAS 1
+#endif
+constexpr int GT_BATCH = UP3D_GT_BATCH;        // rows of a group handled per lane are unrolled in batches of GT_BATCH
+constexpr int GT_MIN_CTAS = UP3D_GT_MIN_CTAS;  // resident CTAs per SM the register budget is sized for
 
 struct GroupTileArgs {
     int Gt, K, C, gpc;
@@ -285,11 +301,41 @@ struct GroupTileArgs {
 
 enum { GT_STATS = 0, GT_APPLY = 1, GT_BWD_REDUCE = 2, GT_BWD_APPLY = 3, GT_MAX = 4, GT_SCATTER = 5, GT_COMBINE = 6 };
 
-template <typename AT, int MODE>
-__global__ void __launch_bounds__(512)
+// ---- bulk-async staging (STAGED variant): a group's K x C tile is ONE contiguous block of memory when the CTA spans all
+// columns, so the CTA streams whole group tiles into a ring of shared-memory stages with cp.async.bulk (one elected
+// thread, completion on an mbarrier) and computes from shared memory.  GT_STAGES tiles (per input) are in flight per SM
+// at all times, without holding them in registers: the direct-load variant ran load -> wait -> compute -> barrier per
+// group and reached ~1.5 TB/s (45 us for the 67 MB of the backward-reduce pass).
+constexpr int GT_STAGES = 3;
+constexpr int GT_BAR_BYTES = 128;
+
+__device__ __forceinline__ uint32_t gt_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gt_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gt_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gt_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gt_smem_u32(dst)), "l"(src), "r"(bytes), "r"(gt_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(gt_smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+template <int MODE> struct GtInputs { static constexpr int N = (MODE == 2 || MODE == 3) ? 2 : (MODE == 5 ? 0 : 1); };
+
+template <typename AT, int MODE, bool STAGED>
+__global__ void __launch_bounds__(512, GT_MIN_CTAS)
 group_tile_kernel(GroupTileArgs A) {
     __shared__ float4 sh0[GT_RL][128];
     __shared__ float4 sh1[GT_RL][128];
+    extern __shared__ __align__(128) uint8_t gt_dyn[];
     const int ct = threadIdx.x, lane_r = threadIdx.y;
     const int col = (blockIdx.y * blockDim.x + ct) * 4;
     const bool col_ok = col < A.C;
@@ -316,7 +362,7 @@ group_tile_kernel(GroupTileArgs A) {
     float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;       // per-CTA partial sums (STATS / BWD_REDUCE / COMBINE)
     const int g_begin = blockIdx.x * A.gpc, g_end = min(A.Gt, g_begin + A.gpc);
     float4 shift = make_float4(0.f, 0.f, 0.f, 0.f);             // STATS: z of the CTA's first row (same for all row lanes)
-    if (MODE == GT_STATS && col_ok) {
+    if (MODE == GT_STATS && col_ok && !STAGED) {
         shift = PVec4<AT>::load(in0 + (size_t)g_begin * K * C + col);
         shift.x += bias.x; shift.y += bias.y; shift.z += bias.z; shift.w += bias.w;
         if (A.gpart) {
@@ -324,7 +370,40 @@ group_tile_kernel(GroupTileArgs A) {
             shift.x += t.x; shift.y += t.y; shift.z += t.z; shift.w += t.w;
         }
     }
+    constexpr int NIN = GtInputs<MODE>::N;
+    const uint32_t tile_bytes = (uint32_t)K * (uint32_t)C * (uint32_t)sizeof(AT);
+    uint64_t *full = reinterpret_cast<uint64_t *>(gt_dyn);
+    uint8_t *ring = gt_dyn + GT_BAR_BYTES;
+    const bool elected = STAGED && threadIdx.x == 0 && threadIdx.y == 0;
+    auto issue = [&](int g, int st) {                               // elected thread: group g's tile(s) -> stage st
+        gt_mbar_expect_tx(&full[st], NIN * tile_bytes);
+        gt_bulk_g2s(ring + (size_t)st * NIN * tile_bytes, in0 + (size_t)g * K * C, tile_bytes, &full[st]);
+        if (NIN == 2) gt_bulk_g2s(ring + ((size_t)st * NIN + 1) * tile_bytes, in1 + (size_t)g * K * C, tile_bytes, &full[st]);
+    };
+    if (STAGED) {
+        if (elected) {
+#pragma unroll
+            for (int st = 0; st < GT_STAGES; ++st) gt_mbar_init(&full[st], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (elected)
+            for (int st = 0; st < GT_STAGES && g_begin + st < g_end; ++st) issue(g_begin + st, st);
+    }
+    if (MODE == GT_STATS && col_ok && STAGED) {                     // (the unstaged variant read it from global above)
+        gt_mbar_wait(&full[0], 0);
+        shift = PVec4<AT>::load(reinterpret_cast<const AT *>(ring) + col);
+        shift.x += bias.x; shift.y += bias.y; shift.z += bias.z; shift.w += bias.w;
+        if (A.gpart) {
+            const float4 t = *reinterpret_cast<const float4 *>(A.gpart + (size_t)g_begin * C + col);
+            shift.x += t.x; shift.y += t.y; shift.z += t.z; shift.w += t.w;
+        }
+    }
     for (int g = g_begin; g < g_end; ++g) {
+        const int it = g - g_begin, stg = it % GT_STAGES;
+        const AT *s0 = reinterpret_cast<const AT *>(ring + (size_t)stg * NIN * tile_bytes);
+        const AT *s1 = reinterpret_cast<const AT *>(ring + ((size_t)stg * NIN + 1) * tile_bytes);
+        if (STAGED) gt_mbar_wait(&full[stg], (uint32_t)((it / GT_STAGES) & 1));
         float4 gp = bias;                                         // broadcast term of this group: gpart + bias
         if (col_ok && A.gpart) {
             const float4 t = *reinterpret_cast<const float4 *>(A.gpart + (size_t)g * C + col);
@@ -339,41 +418,49 @@ group_tile_kernel(GroupTileArgs A) {
         float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         int4 bidx = make_int4(0, 0, 0, 0);
         float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);             // group sum (BWD_APPLY)
-        for (int kb = lane_r; kb < K; kb += GT_RL * 8) {
-            float4 u[8], v[8];
+        constexpr int NB = STAGED ? 4 : GT_BATCH;     // rows in flight per lane (shared-memory reads need few)
+        for (int kb = lane_r; kb < K; kb += GT_RL * NB) {
+            float4 u[NB], v[NB];
             if (MODE != GT_SCATTER) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < NB; ++i) {
                     const int k = kb + i * GT_RL;
                     if (k < K && col_ok) {
-                        const size_t o = ((size_t)g * K + k) * C + col;
-                        u[i] = PVec4<AT>::load(in0 + o);
-                        if (MODE == GT_BWD_REDUCE || MODE == GT_BWD_APPLY) v[i] = PVec4<AT>::load(in1 + o);
+                        if (STAGED) {
+                            const size_t so = (size_t)k * C + col;
+                            u[i] = PVec4<AT>::load(s0 + so);
+                            if (MODE == GT_BWD_REDUCE || MODE == GT_BWD_APPLY) v[i] = PVec4<AT>::load(s1 + so);
+                        } else {
+                            const size_t o = ((size_t)g * K + k) * C + col;
+                            u[i] = PVec4<AT>::load(in0 + o);
+                            if (MODE == GT_BWD_REDUCE || MODE == GT_BWD_APPLY) v[i] = PVec4<AT>::load(in1 + o);
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < NB; ++i) {
                 const int k = kb + i * GT_RL;
                 if (k >= K || !col_ok) continue;
                 const size_t o = ((size_t)g * K + k) * C + col;
+                const float4 ui = u[i], vi = v[i];
                 if (MODE == GT_STATS) {
-                    const float z0 = u[i].x + gp.x - shift.x, z1 = u[i].y + gp.y - shift.y;
-                    const float z2 = u[i].z + gp.z - shift.z, z3 = u[i].w + gp.w - shift.w;
+                    const float z0 = ui.x + gp.x - shift.x, z1 = ui.y + gp.y - shift.y;
+                    const float z2 = ui.z + gp.z - shift.z, z3 = ui.w + gp.w - shift.w;
                     p0.x += z0; p0.y += z1; p0.z += z2; p0.w += z3;
                     p1.x = fmaf(z0, z0, p1.x); p1.y = fmaf(z1, z1, p1.y); p1.z = fmaf(z2, z2, p1.z); p1.w = fmaf(z3, z3, p1.w);
                 } else if (MODE == GT_APPLY) {
                     float4 y;
-                    y.x = fmaxf(fmaf(a.x, u[i].x + gp.x, d.x), 0.f);
-                    y.y = fmaxf(fmaf(a.y, u[i].y + gp.y, d.y), 0.f);
-                    y.z = fmaxf(fmaf(a.z, u[i].z + gp.z, d.z), 0.f);
-                    y.w = fmaxf(fmaf(a.w, u[i].w + gp.w, d.w), 0.f);
+                    y.x = fmaxf(fmaf(a.x, ui.x + gp.x, d.x), 0.f);
+                    y.y = fmaxf(fmaf(a.y, ui.y + gp.y, d.y), 0.f);
+                    y.z = fmaxf(fmaf(a.z, ui.z + gp.z, d.z), 0.f);
+                    y.w = fmaxf(fmaf(a.w, ui.w + gp.w, d.w), 0.f);
                     PVec4<AT>::store(out + o, y);
                 } else if (MODE == GT_BWD_REDUCE || MODE == GT_BWD_APPLY) {
                     // u = dy (gradient of the ReLU output), v = zl (pre-BN local GEMM output)
-                    const float z0 = v[i].x + gp.x, z1 = v[i].y + gp.y, z2 = v[i].z + gp.z, z3 = v[i].w + gp.w;
-                    const float g0 = fmaf(a.x, z0, d.x) > 0.f ? u[i].x : 0.f, g1 = fmaf(a.y, z1, d.y) > 0.f ? u[i].y : 0.f;
-                    const float g2 = fmaf(a.z, z2, d.z) > 0.f ? u[i].z : 0.f, g3 = fmaf(a.w, z3, d.w) > 0.f ? u[i].w : 0.f;
+                    const float z0 = vi.x + gp.x, z1 = vi.y + gp.y, z2 = vi.z + gp.z, z3 = vi.w + gp.w;
+                    const float g0 = fmaf(a.x, z0, d.x) > 0.f ? ui.x : 0.f, g1 = fmaf(a.y, z1, d.y) > 0.f ? ui.y : 0.f;
+                    const float g2 = fmaf(a.z, z2, d.z) > 0.f ? ui.z : 0.f, g3 = fmaf(a.w, z3, d.w) > 0.f ? ui.w : 0.f;
                     const float h0 = (z0 - mean.x) * rstd.x, h1 = (z1 - mean.y) * rstd.y;
                     const float h2 = (z2 - mean.z) * rstd.z, h3 = (z3 - mean.w) * rstd.w;
                     if (MODE == GT_BWD_REDUCE) {
@@ -387,15 +474,15 @@ group_tile_kernel(GroupTileArgs A) {
                         gs.x += dz.x; gs.y += dz.y; gs.z += dz.z; gs.w += dz.w;
                     }
                 } else if (MODE == GT_MAX) {
-                    if (u[i].x > best.x) { best.x = u[i].x; bidx.x = k; }
-                    if (u[i].y > best.y) { best.y = u[i].y; bidx.y = k; }
-                    if (u[i].z > best.z) { best.z = u[i].z; bidx.z = k; }
-                    if (u[i].w > best.w) { best.w = u[i].w; bidx.w = k; }
+                    if (ui.x > best.x) { best.x = ui.x; bidx.x = k; }
+                    if (ui.y > best.y) { best.y = ui.y; bidx.y = k; }
+                    if (ui.z > best.z) { best.z = ui.z; bidx.z = k; }
+                    if (ui.w > best.w) { best.w = ui.w; bidx.w = k; }
                 } else if (MODE == GT_SCATTER) {
                     PVec4<AT>::store(out + o, make_float4(am.x == k ? small.x : 0.f, am.y == k ? small.y : 0.f,
                                                           am.z == k ? small.z : 0.f, am.w == k ? small.w : 0.f));
                 } else if (MODE == GT_COMBINE) {
-                    float4 y = u[i];
+                    float4 y = ui;
                     if (am.x == k) y.x += small.x;
                     if (am.y == k) y.y += small.y;
                     if (am.z == k) y.z += small.z;
@@ -437,6 +524,13 @@ group_tile_kernel(GroupTileArgs A) {
                 }
             }
         }
+        if (STAGED && g + GT_STAGES < g_end) {                   // every thread is done with this stage: refill it
+            __syncthreads();
+            if (elected) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(g + GT_STAGES, stg);
+            }
+        }
     }
     if (MODE == GT_STATS || MODE == GT_BWD_REDUCE || MODE == GT_COMBINE) {
         __syncthreads();
@@ -464,8 +558,21 @@ group_tile_kernel(GroupTileArgs A) {
     }
 }
 
+// Staged (bulk-async ring) when the CTA spans all columns (a group tile is then contiguous), the tile is 16-byte granular,
+// the ring fits and a CTA has several groups to pipeline; UP3D_GT_STAGED=0 keeps the direct-load variant.
+static std::atomic<int> g_gt_staged{-1};         // -1: not decided yet (environment), 0 / 1: off / on
+static bool gt_staged_enabled() {
+    int v = g_gt_staged.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("UP3D_GT_STAGED");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_gt_staged.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
+
 template <typename AT, int MODE>
-static void launch_group_tile(const GroupTileArgs &A, cudaStream_t st) {
+static int launch_group_tile(const GroupTileArgs &A, cudaStream_t st) {
     const int cthreads = A.C / 4;
     int ct = cthreads <= 128 ? cthreads : 128;
     if (cthreads > 128) {
@@ -473,7 +580,21 @@ static void launch_group_tile(const GroupTileArgs &A, cudaStream_t st) {
             if (cthreads % t == 0) { ct = t; break; }
     }
     const dim3 block(ct, GT_RL), grid(div_up(A.Gt, A.gpc), div_up(cthreads, ct));
-    group_tile_kernel<AT, MODE><<<grid, block, 0, st>>>(A);
+    constexpr int NIN = GtInputs<MODE>::N;
+    const size_t tile_bytes = (size_t)A.K * A.C * sizeof(AT);
+    const size_t dyn = GT_BAR_BYTES + (size_t)GT_STAGES * NIN * tile_bytes;
+    if (NIN > 0 && gt_staged_enabled() && grid.y == 1 && A.gpc >= 2 && tile_bytes % 16 == 0 && dyn <= 200 * 1024) {
+        static std::atomic<size_t> configured{0};
+        if (dyn > configured.load(std::memory_order_acquire)) {
+            UP3D_CUDA_OK(cudaFuncSetAttribute((const void *)group_tile_kernel<AT, MODE, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured.store(dyn, std::memory_order_release);
+        }
+        group_tile_kernel<AT, MODE, true><<<grid, block, dyn, st>>>(A);
+    } else {
+        group_tile_kernel<AT, MODE, false><<<grid, block, 0, st>>>(A);
+    }
+    return 0;
 }
 
 }  // namespace up3d
@@ -548,6 +669,12 @@ extern "C" int up3d_bn_reduce_finalize(int n_partials, int C, const float *parti
 }
 
 /* ---- group-tile passes ---- */
+extern "C" int up3d_set_group_tile_staging(int on) {
+    const bool prev = gt_staged_enabled();
+    g_gt_staged.store(on ? 1 : 0, std::memory_order_relaxed);
+    return prev ? 1 : 0;
+}
+
 static int gt_common(const char *name, int Gt, int K, int C, int gpc) {
     UP3D_CHECK_ARG(Gt > 0 && K > 0 && C > 0 && C % 4 == 0 && gpc > 0, "%s: bad sizes Gt=%d K=%d C=%d", name, Gt, K, C);
     UP3D_CHECK_ARG(C / 4 <= 128 || (C / 4) % 32 == 0, "%s: C=%d not supported", name, C);
@@ -556,8 +683,9 @@ static int gt_common(const char *name, int Gt, int K, int C, int gpc) {
 
 #define GT_DISPATCH(MODE)                                         \
     do {                                                          \
-        if (act_bf16) launch_group_tile<__nv_bfloat16, MODE>(A, (cudaStream_t)stream); \
-        else launch_group_tile<float, MODE>(A, (cudaStream_t)stream);                  \
+        int rc_ = act_bf16 ? launch_group_tile<__nv_bfloat16, MODE>(A, (cudaStream_t)stream) \
+                           : launch_group_tile<float, MODE>(A, (cudaStream_t)stream);       \
+        if (rc_) return rc_;                                      \
     } while (0)
 
 extern "C" int up3d_gbn_stats(int act_bf16, int Gt, int K, int C, int gpc, const void *zl, const float *gpart, const float *bias,
@@ -617,7 +745,8 @@ extern "C" int up3d_group_max(int act_bf16, int Gt, int K, int C, const void *x,
     if (int rc = gt_common("up3d_group_max", Gt, K, C, 1)) return rc;
     UP3D_CHECK_ARG(x && out && arg && pn_aligned16(x) && pn_aligned16(out) && pn_aligned16(arg), "up3d_group_max: NULL or misaligned pointer");
     GroupTileArgs A{};
-    A.Gt = Gt; A.K = K; A.C = C; A.gpc = 1; A.in0 = x; A.small_out = out; A.arg_out = arg;
+    // no per-CTA partials here, so the groups-per-CTA split is free: one wave of CTAs, each pipelining its groups
+    A.Gt = Gt; A.K = K; A.C = C; A.gpc = act_bf16 ? (Gt + UP3D_NUM_SMS - 1) / UP3D_NUM_SMS : 1; A.in0 = x; A.small_out = out; A.arg_out = arg;
     GT_DISPATCH(GT_MAX);
     UP3D_LAUNCH_OK("group_tile_kernel<max>");
     return 0;

@@ -114,7 +114,9 @@ class MiniPointNetFn(torch.autograd.Function):
             else:
                 gpart = torch.mm(fg, W3g.t(), out_dtype=torch.float32)              # (Gt, C3) fp32
             zl = f @ W3l.t()                                                        # (R, C3)
-            gpc = 2 if Gt >= 4 * _NUM_SMS else 1
+            # groups per CTA of the group-tile passes.  bf16: one wave of CTAs, each streaming its groups through a
+            # shared-memory ring (csrc/pointnet.cu, STAGED); fp32: short CTAs with direct loads
+            gpc = max(1, -(-Gt // _NUM_SMS)) if act == torch.bfloat16 else (2 if Gt >= 4 * _NUM_SMS else 1)
             n2 = (Gt + gpc - 1) // gpc
             part2 = torch.empty((n2, 3, C3), dtype=torch.float32, device=dev)
             check(L.up3d_gbn_stats(fl, Gt, K, C3, gpc, ptr(zl), ptr(gpart), ptr(b3), ptr(part2), stream_ptr()), 1)
