@@ -12,9 +12,11 @@ from unipre3d_b200 import synthetic
 from unipre3d_b200.trainer import Trainer
 
 
-def run(lookahead: bool, tc: bool = True):
+def run(lookahead: bool, tc: bool = True, tc_all: bool = False):
     dev = torch.device("cuda", 0)
     os.environ["UP3D_TC_LINEAR"] = "1" if tc else "0"
+    from unipre3d_b200 import fused_encoder as fe
+    fe._TC_ALL = tc_all
     if lookahead:
         os.environ.pop("UP3D_NO_LOOKAHEAD", None)
     else:
@@ -40,15 +42,15 @@ def run(lookahead: bool, tc: bool = True):
             b.record()
         torch.cuda.synchronize()
         out.append(sum(a.elapsed_time(b) for a, b in ev) / K)
-    tag = ("lookahead" if tr._la is not None else "inline   ") + (" tcgen05-fc1" if tc else " library-fc1")
+    tag = ("lookahead" if tr._la is not None else "inline   ") + (" tcgen05-all" if (tc and tc_all) else " tcgen05-fc1" if tc else " library-fc1")
     print(tag, "flush + per-step events, 4 x 20 steps:", " ".join(f"{x:.4f}" for x in out), "loss", float(tr._loss_buf), flush=True)
     tr._graph = None
     del tr
 
 
 def main():
-    for la, tc in ((True, True), (True, False), (True, True), (True, False), (False, True)):
-        run(la, tc)
+    for la, tc, ta in ((True, True, False), (True, True, False), (False, True, False)):
+        run(la, tc, ta)
 
 
 if __name__ == "__main__":

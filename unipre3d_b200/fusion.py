@@ -28,14 +28,34 @@ class LazyImageFeatures:
         self.gn, self.conv = image_conv[0], image_conv[1]   # .shape / .dense() / .group_stats(G) / .gather(b, ix, iy)
         self.shape = (decoder_features.shape[0], self.conv.out_channels, *decoder_features.shape[2:])
 
-    def prefetch_stats(self) -> None:
+    def prefetch_stats(self, c2w=None) -> None:
         """Analytic field on CUDA: start the GroupNorm-statistics kernel now, on the side stream, so it runs beside the
-        tokenizer's farthest-point sampling (64 busy SMs, ~100 us) instead of after the transformer."""
+        tokenizer instead of after the transformer.  `c2w`: the source cameras' (B[,views],4,4) row-vector camera-to-world
+        matrices; their inverse (FeatureFusion's world-to-camera, a 9-kernel LU solve of ~28 us that depends on the
+        input alone) is computed on the side stream as well and handed out by take_w2c()."""
         if torch.is_tensor(self.x) or not self.x.image.is_cuda or FORCE_MODULE_PATH:
             return
         from .fused_encoder import SideStream
         self._side = SideStream(self.x.image.device)
-        self._sums = self._side.run(lambda img: self.x.group_sums(self.gn.num_groups), self.x.image)
+        if c2w is not None and c2w.is_cuda:
+            c2w = c2w[:, 0] if c2w.dim() == 4 else c2w
+
+            def both(img, m):
+                return self.x.group_sums(self.gn.num_groups), world_to_camera(m)
+            self._sums, w2c = self._side.run(both, self.x.image, c2w)
+            self._w2c = (c2w, w2c)
+        else:
+            self._sums = self._side.run(lambda img: self.x.group_sums(self.gn.num_groups), self.x.image)
+
+    def take_w2c(self, c2w):
+        """World-to-camera matrices of `c2w` (B,4,4): the prefetched ones when they were computed from this very tensor
+        (call take_stats() first: it joins the side stream), else computed now."""
+        cached = getattr(self, "_w2c", None)
+        if cached is not None and getattr(self, "_side", None) is None:
+            src, w2c = cached
+            if src.data_ptr() == c2w.data_ptr() and src.shape == c2w.shape and src.stride() == c2w.stride() and src.dtype == c2w.dtype:
+                return w2c
+        return world_to_camera(c2w)
 
     def take_stats(self):
         """-> sums (n,G,2) fp64, joined with the current stream."""
@@ -71,6 +91,12 @@ class LazyImageFeatures:
         return torch.nn.functional.linear(y, conv.weight.reshape(conv.out_channels, Cin), conv.bias)
 
 
+def world_to_camera(c2w):
+    """(B,4,4) row-vector camera-to-world -> column-vector world-to-camera, fp32 (feat_fusion.py:30-33)."""
+    with torch.no_grad(), torch.autocast(c2w.device.type, enabled=False):
+        return torch.linalg.inv_ex(c2w.permute(0, 2, 1).float()).inverse.contiguous()   # inv() without its blocking info check
+
+
 FORCE_MODULE_PATH = False      # tests: run the eager restatement below on CUDA too
 FUSED_MAX_POINTS = 1024        # centres per object the fused kernel holds in shared memory
 
@@ -88,8 +114,8 @@ def fused_project_and_sample(lazy: "LazyImageFeatures", center, c2w_matrix, intr
     G = gn.num_groups
     dev = center.device
     with torch.no_grad(), torch.autocast("cuda", enabled=False):
-        w2c = torch.linalg.inv_ex(c2w_matrix.permute(0, 2, 1).float()).inverse.contiguous()
-        sums = lazy.take_stats()
+        sums = lazy.take_stats()                  # joins the side stream that also inverted the camera matrices
+        w2c = lazy.take_w2c(c2w_matrix)
         keep = torch.empty((B, N), dtype=torch.uint8, device=dev)
         pix = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
         xhat = torch.empty((B, N, Cin), dtype=torch.float32, device=dev)

@@ -328,7 +328,7 @@ class GaussianSplatPredictor(nn.Module):
         else:
             image_output = self.image_network.forward(image, lazy=True)
             image_features = LazyImageFeatures(image_output["decoder_block_3"], self.image_conv)
-            image_features.prefetch_stats()
+            image_features.prefetch_stats(source_cameras_view_to_world)
         point_features, center = self.point_network.forward_feat_fusion(
             point_cloud, image_features, source_cameras_view_to_world, self.fusion_mlps, self.intrinsic)
         if point_features.is_cuda and not getattr(self, "force_module_path", False):

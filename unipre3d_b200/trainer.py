@@ -24,7 +24,7 @@ import torch.distributed as dist
 
 from .gaussian_predictor import GaussianSplatPredictor
 from .gaussian_renderer import render_batch_predicted
-from .loss import focal_l2_loss, l1_loss, l2_loss
+from .loss import focal_l2_loss, l1_loss, l2_loss, backward_unit
 
 
 def _to_device(x, device, non_blocking=True):
@@ -375,7 +375,7 @@ class Trainer:
             after_forward()
         rendered, gt = self.render_validation_views(splats, data)
         loss = self.validation_manager.calculate_losses(rendered, gt, self.iteration)["total_loss"]
-        loss.backward()
+        backward_unit(loss)
         return loss.detach()
 
     # ------------------------------------------------------------------------------------------ data parallelism
