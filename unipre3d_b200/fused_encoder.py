@@ -163,6 +163,12 @@ GRAD_CHUNK_BLOCKS = 4
 # stack_grad_order() says, or None.  The batched weight-gradient GEMMs and the column-sum kernels then write there
 # directly and the 113 MB pack in front of the all-reduce disappears.
 GRAD_BUFFERS = None
+# Opt-in (UP3D_WGRAD_CHUNK=n > 0): every n blocks (counting down) the four batched weight-gradient GEMMs of those blocks
+# (+ fc1's stacked bias column-sum) are issued on the side stream, beside the dX chain of the blocks in front of them,
+# instead of as 100 us of serial GEMMs after the chain.  Measured (profiles/r2_step_ab.txt): 2.61 / 2.63 / 2.60 ms per
+# step for n = 4 / 2 / 8 against 2.58 ms for the serial batch at the end -- the GEMMs slow the latency-bound chain by
+# more than they hide -- hence 0 (off) by default.
+WGRAD_CHUNK = int(os.environ.get("UP3D_WGRAD_CHUNK", "0"))
 
 
 def stack_grad_order(depth: int):
@@ -303,6 +309,18 @@ class EncoderStackFn(torch.autograd.Function):
             dd = scale_cast_colsum(g, s2_last, L, act, sm(depth - 1, 5), out=DD[depth - 1])
             chunked = GRAD_CHUNK_HOOK is not None and depth % GRAD_CHUNK_BLOCKS == 0
             wg = {}                                 # block index -> (gWqkv, gWproj, gW1, gW2) when produced chunk-wise
+            CH = WGRAD_CHUNK if (WGRAD_CHUNK > 0 and not chunked and depth % max(WGRAD_CHUNK, 1) == 0
+                                 and depth > WGRAD_CHUNK and g.is_cuda) else 0
+            side = SideStream(dev) if CH else None
+
+            def side_wgrads(sl):
+                """(side stream) weight gradients of blocks `sl` into their slabs (exchange buffer or fresh tensors)."""
+                oq, op, o1, o2 = (b[sl] for b in bufs[:4]) if bufs is not None else (None,) * 4
+                c2, c1 = _wgrad_batched(DD[sl], HH[sl], o2), _wgrad_batched(DPRE[sl], Y2[sl], o1)
+                cp, cq = _wgrad_batched(DA[sl], O[sl], op), _wgrad_batched(DQKV[sl], Y1[sl], oq)
+                if tc:
+                    small.view(depth, per)[sl, 6 * C:].copy_(DPRE[sl].sum(dim=1, dtype=torch.float32))
+                return cq, cp, c1, c2
 
             def block_grads(i, gWqkv_i, gWproj_i, gW1_i, gW2_i):
                 return [sm(i, 0), sm(i, 1), gWqkv_i, gWproj_i, sm(i, 2), sm(i, 3), sm(i, 4), gW1_i, sm(i, 6, Hd), gW2_i, sm(i, 5)]
@@ -333,6 +351,11 @@ class EncoderStackFn(torch.autograd.Function):
                 dy1 = _dx_deep(dqkv, wqkv, tc)
                 g, dd = ln_bwd(dy1, xs, mu1, rs1, n1w, dx2, s2_prev, L, dpos, i > 0, sm(i, 0), sm(i, 1),
                                sm(i - 1, 5) if i > 0 else None, scaled_out=DD[i - 1] if i > 0 else None)
+                if CH and i % CH == 0:
+                    sl = slice(i, i + CH)
+                    cq, cp, c1, c2 = side.run(lambda *keep, sl=sl: side_wgrads(sl), DD, HH, DPRE, Y2, DA, O, DQKV, Y1, small)
+                    for k in range(CH):
+                        wg[i + k] = (cq[k], cp[k], c1[k], c2[k])
                 if chunked and i % GRAD_CHUNK_BLOCKS == 0:
                     # data parallel: the weight gradients of blocks [i, i + CH) now, so their all-reduce starts now
                     sl = slice(i, i + GRAD_CHUNK_BLOCKS)
@@ -345,7 +368,9 @@ class EncoderStackFn(torch.autograd.Function):
                         wg[i + k] = (cq[k], cp[k], c1[k], c2[k])
                         chunk += block_grads(i + k, *wg[i + k])
                     GRAD_CHUNK_HOOK(i, chunk)
-            if not chunked:
+            if side is not None:
+                side.join()                         # (only the chunk of the first blocks can still be in flight)
+            elif not chunked:
                 # ---- weight gradients of all blocks: four batched GEMMs (fp32 written by the GEMM)
                 oq, op, o1, o2 = bufs[:4] if bufs is not None else (None,) * 4
                 gW2, gW1 = _wgrad_batched(DD, HH, o2), _wgrad_batched(DPRE, Y2, o1)
