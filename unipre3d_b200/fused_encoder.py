@@ -183,6 +183,9 @@ def stack_grad_order(depth: int):
     return order
 
 
+SIDE_STREAM_INLINE = os.environ.get("UP3D_SIDE_INLINE", "0") != "0"
+
+
 class SideStream:
     """Runs work that is OFF the backward critical path (the weight-gradient GEMMs: nothing downstream in the backward
     needs them) on a second stream, so their launch latency and tails overlap the dX chain -- at 1032 tokens every GEMM of
@@ -198,6 +201,8 @@ class SideStream:
         self.keep = []
 
     def run(self, fn, *tensors):
+        if SIDE_STREAM_INLINE:                      # (A/B switch: run the work in line on the current stream)
+            return fn(*tensors)
         self.side.wait_stream(self.main)
         with torch.cuda.stream(self.side):
             out = fn(*tensors)
@@ -205,6 +210,9 @@ class SideStream:
         return out
 
     def join(self):
+        if SIDE_STREAM_INLINE:
+            self.keep.clear()
+            return
         self.main.wait_stream(self.side)
         self.keep.clear()
 
