@@ -51,19 +51,60 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  In-process NVML
+    (what nvidia-smi itself reads) from one background thread, every 100 ms; falls back to an `nvidia-smi -lms` child when
+    NVML cannot be loaded.  `enabled=False` (ranks other than 0 of a multi-GPU run) samples nothing: eight `nvidia-smi`
+    pollers on one box take driver locks often enough to stall the ranks' launches, and with the per-step all-reduce one
+    stalled rank stalls all of them (N = 8 end-to-end step: 10 ms with a poller per rank)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index: int, enabled: bool = True):
+        self.idx, self.proc, self.lines, self.enabled = gpu_index, None, [], enabled
+        self.source, self._stop, self.t = None, threading.Event(), None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(vis[self.idx]) if self.idx < len(vis) else self.idx)
+
+    def _poll_nvml(self, nv, h):
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                f = [str(self.idx), str(sm), str(mx), "", hex(r)] + ["Active" if r & bits[k] else "Not Active"
+                                                                      for k in ("hw_slowdown", "hw_thermal_slowdown",
+                                                                                "sw_thermal_slowdown", "sw_power_cap")]
+                self.lines.append(", ".join(f))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
 
     def __enter__(self):
+        if not self.enabled:
+            return self
+        try:
+            nv, h = self._nvml_handle()
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -75,6 +116,10 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def __exit__(self, *a):
+        if self.source == "nvml":
+            time.sleep(0.12)
+            self._stop.set()
+            self.t.join(timeout=2)
         if self.proc:
             time.sleep(0.25)
             self.proc.terminate()
@@ -97,9 +142,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.source}
 
 
 def ncu_traffic(kernel_substr: str, pattern: str = "*_P128_ncu_raw.csv"):
@@ -504,7 +549,7 @@ def ours(args):
             trainer._step_body(resident)
     for _ in range(2):
         step_resident(0)                       # untimed: the first resident replay groups its batch in line
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
         ms_resident = timed(step_resident)
         # ---- end-to-end steps: pinned host batch -> H2D -> step -> D2H loss, through the public API
         losses = []
