@@ -555,7 +555,7 @@ def ours(args):
         losses = []
         # (the next step's pinned batch is prefetched on a copy stream while this step computes; every step still
         #  moves its full input batch host->device inside the timed region and reads its loss back)
-        #  the loss of every step is read back device->host, consumed with a one-step lag as a logging loop would)
+        #  the loss of every step is read back device->host, consumed with a two-step lag as a logging loop would)
         ms_e2e = timed(lambda i: losses.append(trainer.train_iteration(
             batches[i % n_batches], read_loss="lagged", prefetch=batches[(i + 1) % n_batches])))
         losses = [x for x in losses if x is not None] + [trainer.last_loss()]

@@ -321,8 +321,12 @@ class Trainer:
                           f"raises there (set opt.lambda_lpips=0 to train without it)", stacklevel=2)
         self._loss_buf = torch.zeros((), dtype=torch.float32, device=self.device)
         self._loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-        self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self._loss_ev = [None, None]
+        # lagged loss reads: step i's loss is read back when step i + LOSS_LAG is enqueued, so the host may run LOSS_LAG
+        # steps ahead of the device (data parallel: a rank whose host hiccups for a millisecond then no longer stalls
+        # every rank through the per-step all-reduce)
+        self.LOSS_LAG = 2
+        self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(self.LOSS_LAG + 1)]
+        self._loss_ev = [None] * (self.LOSS_LAG + 1)
         # input pipelining: the next batch is copied host->device on a side stream while the current step runs
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._staged = None          # (key, device dict | flat device buffer, ready event)
@@ -719,18 +723,22 @@ class Trainer:
         if mm.ema:
             mm.ema.update()
         if read_loss == "lagged":
-            # D2H read of THIS step's loss is enqueued now and consumed one step later (logging lags by one step),
-            # so the host never stalls the launch pipeline; returns the previous step's loss (None on the first call)
-            slot = self.iteration & 1
+            # D2H read of THIS step's loss is enqueued now and consumed LOSS_LAG steps later (logging lags), so the host
+            # never stalls the launch pipeline; returns the loss of step (this - LOSS_LAG) (None on the first calls)
+            n = self.LOSS_LAG + 1
+            slot = self.iteration % n
+            old_slot = (self.iteration + 1) % n            # = (iteration - LOSS_LAG) mod n: the oldest read in flight
+            prev = self._loss_ev[old_slot]
+            out = None
+            if prev is not None:
+                prev.synchronize()
+                out = float(self._loss_ring[old_slot])
+                self._loss_ev[old_slot] = None
             self._loss_ring[slot].copy_(loss, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             self._loss_ev[slot] = ev
-            prev = self._loss_ev[slot ^ 1]
-            if prev is None:
-                return None
-            prev.synchronize()
-            return float(self._loss_ring[slot ^ 1])
+            return out
         if read_loss:
             self._loss_host.copy_(loss, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -739,7 +747,7 @@ class Trainer:
 
     def last_loss(self) -> float:
         """Blocks for the most recent step's lagged loss read."""
-        slot = self.iteration & 1
+        slot = self.iteration % (self.LOSS_LAG + 1)
         if self._loss_ev[slot] is None:
             raise RuntimeError("no lagged loss read in flight")
         self._loss_ev[slot].synchronize()
