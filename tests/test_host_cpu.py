@@ -366,3 +366,22 @@ def test_stack_grad_order_is_the_backward_slab_layout():
     assert sorted(order) == list(range(depth * P))
     assert order[:depth] == [2, 2 + P, 2 + 2 * P] and order[3 * depth:4 * depth] == [9, 9 + P, 9 + 2 * P]
     assert order[4 * depth:4 * depth + 7] == [0, 1, 4, 5, 6, 10, 8]
+
+
+def test_clock_sampler_summary_and_disabled_rank():
+    """bench.ClockSampler: parsing of the sampled lines (median SM clock, max clock, throttle reasons) and the disabled
+    sampler of ranks > 0 (no thread, no child process, empty summary)."""
+    import bench
+    c = bench.ClockSampler(0, enabled=False)
+    with c:
+        pass
+    assert c.proc is None and c.t is None
+    assert c.summary() == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+    c.lines = ["0, 1965, 1965, , 0x0, Not Active, Not Active, Not Active, Not Active",
+               "0, 1950, 1965, , 0x4, Not Active, Not Active, Not Active, Active",
+               "0, 1935, 1965, , 0x0, Not Active, Not Active, Not Active, Not Active",
+               "garbage"]
+    c.source = "nvml"
+    out = c.summary()
+    assert out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"] and out["source"] == "nvml"
