@@ -27,7 +27,7 @@ def run(name, fn, n=40):
     print(f"{name:40s} {(time.perf_counter() - t0) / n * 1e3:.3f} ms/step (wall)", flush=True)
 
 
-run("graph replay only", lambda i: tr._graph.replay())
+run("graph replay only", lambda i: tr.replay_resident())
 run("lagged loss + prefetch", lambda i: tr.train_iteration(batches[i % 4], read_loss="lagged", prefetch=batches[(i + 1) % 4]))
 run("no loss read + prefetch", lambda i: tr.train_iteration(batches[i % 4], read_loss=False, prefetch=batches[(i + 1) % 4]))
 run("lagged loss, no prefetch", lambda i: tr.train_iteration(batches[i % 4], read_loss="lagged"))
@@ -56,6 +56,6 @@ def timed(name, step_fn, n=20):
     print(f"{name:40s} events {sum(per) / n:.3f} ms/step  wall {wall:.3f}  min {min(per):.3f} max {max(per):.3f}", flush=True)
 
 
-timed("flush + graph replay", lambda i: tr._graph.replay())
+timed("flush + graph replay", lambda i: tr.replay_resident())
 timed("flush + e2e lagged/prefetch", lambda i: tr.train_iteration(batches[i % 4], read_loss="lagged", prefetch=batches[(i + 1) % 4]))
 timed("flush + e2e no-loss/prefetch", lambda i: tr.train_iteration(batches[i % 4], read_loss=False, prefetch=batches[(i + 1) % 4]))

@@ -29,7 +29,7 @@ for branch in ("sdvae", "stem"):
     t0 = time.perf_counter()
     n = 20
     for _ in range(n):
-        tr._graph.replay()
+        tr.replay_resident()
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / n * 1e3
     print(f"image_branch={branch}: {ms:.3f} ms/step -> {32 / ms * 1e3:.0f} views/s (graph replays, resident inputs)", flush=True)
